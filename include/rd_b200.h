@@ -1,0 +1,148 @@
+/*
+ * rd_b200.h — C ABI of the B200-native RiboDetector hot path (librd_b200.so).
+ *
+ * The reference (hzi-bifo/RiboDetector, pure Python) has no FFI; its plugin seam for this path
+ * is the object that `ConfigParser.init_obj('arch', module)` builds
+ * (ribodetector/parse_config.py:43-57, called at ribodetector/detect.py:93) plus the collate
+ * function that feeds it (detect.py:666-726).  Each entry point below cites the reference
+ * interface it replaces.  The Python side (ribodetector_b200/model/model.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer; the library owns the handle
+ *     (device weight images, LUTs, scratch).  Nothing allocated here is returned to the caller.
+ *   - every function returns RD_OK (0) or an RD_ERR_* code and never throws; the message is
+ *     available from rd_last_error().
+ *   - reads are passed as a byte concatenation `seq` plus `off[n+1]` (int64, off[0] may be
+ *     non-zero; read i is seq[off[i] .. off[i+1])).  Bytes are the sequence line as it
+ *     appears in the FASTQ/FASTA record; the encoding table is the reference's BASE_DICT.
+ *   - "d_" parameters are device pointers on the handle's device; functions taking a `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) are asynchronous on it.
+ *   - a handle is bound to one device; calls on one handle must not overlap (thread-compatible,
+ *     not re-entrant), mirroring the reference's single model object per process.
+ */
+#ifndef RD_B200_H
+#define RD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rd_handle rd_handle;
+
+#define RD_ABI_VERSION 1
+
+/* return codes */
+#define RD_OK               0
+#define RD_ERR_INVALID      1   /* bad argument (maps to ValueError in the Python wrapper)      */
+#define RD_ERR_CUDA         2   /* CUDA runtime failure / no device (RuntimeError)             */
+#define RD_ERR_EMPTY_READ   3   /* zero-length read under packed semantics: torch's            */
+                                /* pack_sequence raises on it too (detect.py:685) → RuntimeError*/
+#define RD_ERR_NOMEM        4
+#define RD_ERR_UNSUPPORTED  5   /* shape outside what the kernels were built for               */
+
+/* which "last valid step" convention:
+ *   PACKED  = `ribodetector`     : detect.py:681-685 + model/model.py:32-37,114-119
+ *   PADDED  = `ribodetector_cpu` : detect_cpu.py:699-703 + model/model_cpu.py:29-37,57-62     */
+#define RD_SEM_PACKED 0
+#define RD_SEM_PADDED 1
+
+/* arithmetic of the forward-direction recurrent contraction
+ *   FP32     : fp32 FFMA on CUDA cores, accurate exp/tanh — the on-device fp32 reference
+ *   TC_EXACT : tcgen05 kind::f16, fp16 hi/lo split of W_hh and h_t (3 MMA passes, fp32
+ *              accumulate in TMEM), fp32 activations
+ *   TC_FAST  : tcgen05 kind::f16, single pass, approximate activations                       */
+#define RD_PREC_FP32     0
+#define RD_PREC_TC_EXACT 1
+#define RD_PREC_TC_FAST  2
+
+/* paired-end combination, detect.py:616-663 (`-e/--ensure`) */
+#define RD_PAIR_NONE   0   /* argmax(logits_r1 + logits_r2)            detect.py:655-661 */
+#define RD_PAIR_RRNA   1   /* 1 iff both ends 1                        detect.py:620-630 */
+#define RD_PAIR_NORRNA 2   /* 0 iff both ends 0                        detect.py:631-641 */
+#define RD_PAIR_BOTH   3   /* concordant label else -1 (unclassified)  detect.py:642-654 */
+
+/* one-hot output layouts of rd_encode_onehot */
+#define RD_ONEHOT_RAGGED 0 /* [sum_i min(len_i,max_len), 4] fp32, read after read in input order:
+                              seq_encoder.py:126-127 encode_read(seq[:max_len]) (detect.py:682) */
+#define RD_ONEHOT_PADDED 1 /* [n, max_len, 4] fp32, zero rows appended:
+                              seq_encoder.py:130-145 encode_variable_len_read                   */
+
+#define RD_MAX_LEN 4096    /* largest supported -l / max_len */
+
+int rd_abi_version(void);
+
+/* Replaces SeqModel.__init__ + load_state_dict + .to('cuda').eval()
+ * (model/model.py:11-29, detect.py:93,115-119).  All weight pointers are HOST fp32 arrays in
+ * the reference state_dict layout: w_ih [4H,4], w_hh [4H,H], b_ih [4H], b_hh [4H] (gate row
+ * order i,f,g,o) for the forward ("_l0") and reverse ("_l0_reverse") directions, w_out [2,2H],
+ * b_out [2].  hidden must be 128.  Uploads the weights, builds the gate-input table, the
+ * tensor-core weight images and the reverse-direction logit LUT on `device`. */
+int rd_create(int device,
+              const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+              const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r,
+              const float* w_out, const float* b_out,
+              int hidden, rd_handle** out);
+
+void rd_destroy(rd_handle* h);
+
+/* message of the last failure on this handle (h == NULL: last failure of rd_create). */
+const char* rd_last_error(const rd_handle* h);
+
+/* Pre-size the scratch for batches of up to n reads of up to max_len steps (optional; the
+ * classify calls grow it on demand, which synchronises the device). */
+int rd_reserve(rd_handle* h, int64_t n, int max_len);
+
+/* Replaces encode_read / encode_variable_len_read (seq_encoder.py:126-145) as called from the
+ * collate functions (detect.py:681-682, detect_cpu.py:699-700).  d_out is fp32, layout above;
+ * d_row_off (RAGGED only, may be NULL) receives int64[n+1] row offsets into d_out. */
+int rd_encode_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n,
+                     int max_len, int layout, float* d_out, int64_t* d_row_off, void* stream);
+
+/* Replaces collate + `model(data)` + argmax for one batch of single reads
+ * (detect.py:284-288: unlabeled_read_collate_fn → SeqModel.forward1 → torch.argmax).
+ * Outputs (each may be NULL): d_logits [n,2] fp32 raw logits in input order (model.py:36-37),
+ * d_probs [n,2] fp32 softmax of the logits, d_labels [n] int8 argmax (ties → 0),
+ * d_counts int64[3] += {#label0 (non-rRNA), #label1 (rRNA), 0}. */
+int rd_classify(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n,
+                int max_len, int semantics, int precision,
+                float* d_logits, float* d_probs, int8_t* d_labels, int64_t* d_counts,
+                void* stream);
+
+/* Replaces Predictor.separate_paired_reads' label rule (detect.py:616-663) for n pairs.
+ * d_labels [n] int8 in {-1,0,1}; d_counts int64[3] += {non-rRNA, rRNA, unclassified} pairs. */
+int rd_pair_combine(rd_handle* h, const float* d_logits1, const float* d_logits2, int64_t n,
+                    int mode, int8_t* d_labels, int64_t* d_counts, void* stream);
+
+/* Host-buffer forms: what the reference's batch loops do per file/chunk (detect.py:284-298 and
+ * :183-206).  Synchronous.  seq/off/outputs are HOST pointers (pinned or pageable); the library
+ * pipelines H2D → kernels → D2H in chunks on its own streams.  counts is int64[3], overwritten.
+ * Outputs may be NULL except labels. */
+int rd_classify_host(rd_handle* h, const uint8_t* seq, const int64_t* off, int64_t n,
+                     int max_len, int semantics, int precision,
+                     float* logits, float* probs, int8_t* labels, int64_t* counts);
+
+int rd_classify_pairs_host(rd_handle* h,
+                           const uint8_t* seq1, const int64_t* off1,
+                           const uint8_t* seq2, const int64_t* off2, int64_t n,
+                           int max_len, int semantics, int precision, int mode,
+                           float* logits1, float* logits2, int8_t* labels, int64_t* counts);
+
+/* Diagnostics: number of kernel launches issued through this handle so far, and the reverse-
+ * direction logit LUT (host copy, fp32 [kmax+1,5,2]) for tests. */
+int64_t rd_kernel_launches(const rd_handle* h);
+int rd_reverse_lut(rd_handle* h, int kmax, float* out);
+
+/* Per-stage device timing for bench.py's roofline: when enabled, every classify / pair call
+ * brackets its stages with CUDA events on the launching stream.  rd_get_timing synchronises the
+ * device and returns accumulated milliseconds and launch counts per stage
+ * (0 = K1 plan/encode, 1 = K2 LSTM, 2 = K3 tail, 3 = pair combine); reset != 0 clears them. */
+int rd_set_timing(rd_handle* h, int enable);
+int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RD_B200_H */

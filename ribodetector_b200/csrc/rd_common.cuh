@@ -1,0 +1,107 @@
+// rd_common.cuh — shared definitions of librd_b200 (handle, layouts, launch bookkeeping).
+//
+// HBM data layout of one classify batch (all scratch is owned by the handle):
+//   d_seq   uint8  [total]            caller's sequence bytes (FASTQ sequence lines, concatenated)
+//   d_off   int64  [n+1]              caller's read offsets into d_seq
+//   plan    uint32 [n]                per read: nfwd (13 b) | krev (13 b) << 13 | crev (3 b) << 26
+//                                     | invalid << 29      (see rd_plan.cu)
+//   perm    int32  [tiles*128]        slot → read index, slots sorted by nfwd DESCENDING
+//                                     (length-bucketed tiles, SURVEY §5 "long-context"); -1 = pad
+//   splan   uint32 [tiles*128]        plan[] gathered into slot order (0 for pad slots)
+//   codes   uint8  [tiles][L][128]    base codes 0..3 = A,C,G,T/U, 4 = zero row, transposed so
+//                                     that the 128 reads of a tile at step t are one 128-B line
+//   logits  fp32   [n][2]             caller's output, input order
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/rd_b200.h"
+
+#define RD_H        128            // hidden size
+#define RD_G4       512            // 4 gates x hidden
+#define RD_TILE     128            // reads per tile (= TMEM lanes = UMMA M)
+
+#define PLAN_NFWD(p)   ((p) & 0x1FFFu)
+#define PLAN_KREV(p)   (((p) >> 13) & 0x1FFFu)
+#define PLAN_CREV(p)   (((p) >> 26) & 0x7u)
+#define PLAN_INVALID(p) (((p) >> 29) & 0x1u)
+
+struct rd_tc_state;                // tensor-core weight images (rd_lstm_tc.cu)
+
+struct rd_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    // weights (device, fp32)
+    float* d_tab_f = nullptr;      // [5][512] fwd gate-input table: W_ih^T rows + b_ih + b_hh; row 4 = bias only
+    float* d_whh_t = nullptr;      // [128][512] W_hh^T (k-major)
+    float* d_tab_r = nullptr;      // [5][512] reverse direction table
+    float* d_whh_r_t = nullptr;    // [128][512]
+    float* d_wout = nullptr;       // [2][256]
+    float* d_bout = nullptr;       // [2]
+    float* d_revlut = nullptr;     // [RD_MAX_LEN][5][2] reverse-half logit contributions
+    rd_tc_state* tc = nullptr;
+
+    // scratch
+    int64_t cap_n = 0;             // reads
+    int64_t cap_slots = 0;         // tiles*128
+    int64_t cap_codes = 0;         // bytes
+    uint32_t* d_plan = nullptr;
+    uint32_t* d_splan = nullptr;
+    int32_t* d_perm = nullptr;
+    uint8_t* d_codes = nullptr;
+    int32_t* d_hist = nullptr;     // [RD_MAX_LEN+2] histogram → bucket starts
+    int32_t* d_cursor = nullptr;   // [RD_MAX_LEN+2]
+    int32_t* d_ctrl = nullptr;     // [8]: 0 = status flags, 1 = work counter, 2 = max nfwd
+    int64_t* d_blocksum = nullptr; // scan scratch for ragged one-hot
+    int64_t cap_blocksum = 0;
+
+    // per-stage timing (rd_set_timing)
+    bool timing = false;
+    struct TimedSpan { cudaEvent_t a, b; int which; };
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double t_ms[4] = {0, 0, 0, 0};
+    int64_t t_cnt[4] = {0, 0, 0, 0};
+
+    // host pipeline (rd_classify_host)
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    static const int NSTAGE = 2;
+    uint8_t* d_stage_seq[2][NSTAGE] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int64_t* d_stage_off[2][NSTAGE] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    float* d_stage_logits[2][NSTAGE] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    float* d_stage_probs[NSTAGE] = {nullptr, nullptr};
+    int8_t* d_stage_labels[NSTAGE] = {nullptr, nullptr};
+    int64_t* d_stage_counts = nullptr;
+    int64_t cap_stage_bytes = 0, cap_stage_n = 0;
+    cudaEvent_t ev_in[NSTAGE] = {nullptr, nullptr}, ev_cmp[NSTAGE] = {nullptr, nullptr},
+                ev_out[NSTAGE] = {nullptr, nullptr};
+};
+
+#define RD_CUDA(h, call)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                \
+            return RD_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+// kernels' host launchers (each returns RD_OK / RD_ERR_*; all async on `st`)
+int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
+                   int semantics, int64_t* n_tiles_out, cudaStream_t st);
+int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
+                     int layout, float* d_out, int64_t* d_row_off, cudaStream_t st);
+int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int max_len, float* d_logits, cudaStream_t st);
+int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int max_len, int precision, float* d_logits,
+                      cudaStream_t st);
+int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_probs, int8_t* d_labels,
+                   int64_t* d_counts, cudaStream_t st);
+int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n, int mode,
+                   int8_t* d_labels, int64_t* d_counts, cudaStream_t st);
+int rd_build_reverse_lut(rd_handle* h, const float* d_wout_full, cudaStream_t st);
+int rd_tc_create(rd_handle* h, const float* w_hh_f_host, const float* tab_f_host);
+void rd_tc_destroy(rd_handle* h);

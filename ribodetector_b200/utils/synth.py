@@ -1,0 +1,36 @@
+"""Deterministic synthetic read generator: numpy PCG64, bases i.i.d. uniform
+over ACGT with 0.1 % of positions replaced by 'N'.  There is no network, so every benchmark
+and parity test runs on reads made here."""
+import numpy as np
+
+_ALPHA = np.frombuffer(b"ACGT", dtype=np.uint8)
+SEED_BASE = 20261017
+
+
+def synth_reads_fixed(n, length, seed, n_frac=0.001):
+    """n reads of exactly `length` bases → (uint8 [n*length], int64 offsets [n+1])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    seq = _ALPHA[rng.integers(0, 4, size=n * length, dtype=np.uint8)]
+    if n_frac > 0 and seq.size:
+        k = rng.binomial(seq.size, n_frac)
+        seq[rng.integers(0, seq.size, size=k)] = ord("N")
+    off = np.arange(n + 1, dtype=np.int64) * length
+    return seq, off
+
+
+def synth_reads(n, min_len, max_len, seed, n_frac=0.001):
+    """n reads with length ~ U{min_len..max_len} → (uint8 bytes, int64 offsets [n+1])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens = rng.integers(min_len, max_len + 1, size=n, dtype=np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    seq = _ALPHA[rng.integers(0, 4, size=int(off[-1]), dtype=np.uint8)]
+    if n_frac > 0 and seq.size:
+        k = rng.binomial(seq.size, n_frac)
+        seq[rng.integers(0, seq.size, size=k)] = ord("N")
+    return seq, off
+
+
+def to_strings(seq, off):
+    b = seq.tobytes()
+    return [b[off[i]:off[i + 1]].decode("latin-1") for i in range(len(off) - 1)]

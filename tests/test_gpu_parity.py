@@ -1,0 +1,235 @@
+"""GPU: the CUDA path through the C ABI against (a) the golden vectors produced by the real
+reference, (b) the oracle on seeded inputs, (c) size-independent properties.
+
+Tolerances (stated once, used everywhere):
+  * one-hot / labels from given logits / pair combination / counts: bit-exact
+  * logits, precision fp32 (CUDA-core) and tc_exact (3-pass fp16 split): |dlogit| <= 2e-4 vs the
+    reference's torch fp32 output, softmax |dp| <= 1e-4; labels identical for every read whose
+    reference margin |l1-l0| > 4e-4 (= 2 x eps), the in-band count is asserted small
+  * precision tc_fast: |dlogit| <= 5e-2, |dp| <= 2e-2, flip rate reported/asserted < 0.1 %
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, split_reads
+from oracle import encoders, pairs
+from oracle.model_numpy import softmax2
+from ribodetector_b200 import _lib
+from ribodetector_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": (2e-4, 1e-4), "tc_exact": (2e-4, 1e-4), "tc_fast": (5e-2, 2e-2)}
+
+
+def built_precisions(model):
+    """Precision modes this library build supports (tensor-core modes land after fp32)."""
+    out = ["fp32"]
+    seq, off = encoders.flatten_reads(["ACGT" * 10] * 4)
+    for p in ("tc_exact", "tc_fast"):
+        try:
+            model.classify(seq, off, 40, precision=p)
+            torch.cuda.synchronize()
+            out.append(p)
+        except _lib.RdError:
+            pass
+    return out
+
+
+def check_logits(got, ref, prec):
+    tol_l, tol_p = TOL[prec]
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    d = np.abs(got - ref).max()
+    dp = np.abs(softmax2(got) - softmax2(ref)).max()
+    assert d <= tol_l, "max |dlogit| %.3e > %.1e (%s)" % (d, tol_l, prec)
+    assert dp <= tol_p, "max |dp| %.3e > %.1e (%s)" % (dp, tol_p, prec)
+    margin = np.abs(ref[:, 1] - ref[:, 0])
+    out_band = margin > 2 * tol_l
+    assert (got.argmax(1) == ref.argmax(1))[out_band].all()
+    return d
+
+
+# ---- K1: encoders ----------------------------------------------------------------------------------
+def test_onehot_matches_reference_golden(gpu_model):
+    g = load_golden("encode")
+    got16 = gpu_model.encode_onehot(g["seq"], g["off"], 16, "padded").cpu().numpy()
+    got100 = gpu_model.encode_onehot(g["seq"], g["off"], 100, "padded").cpu().numpy()
+    assert np.array_equal(got16, g["padded16"])
+    assert np.array_equal(got100, g["padded100"])
+    rows, row_off = gpu_model.encode_onehot(g["seq"], g["off"], 4096, "ragged")
+    assert np.array_equal(rows.cpu().numpy(), g["onehot_rows"])
+    lens = g["off"][1:] - g["off"][:-1]
+    assert np.array_equal(row_off.cpu().numpy(), np.concatenate([[0], np.cumsum(lens)]))
+
+
+def test_onehot_ragged_truncates_and_scans_many_blocks(gpu_model):
+    seq, off = synth.synth_reads(70000, 1, 60, 7, n_frac=0.05)
+    rows, row_off = gpu_model.encode_onehot(seq, off, 37, "ragged")
+    reads = synth.to_strings(seq, off)
+    want = np.concatenate([encoders.encode_read(r[:37]) for r in reads], 0)
+    assert np.array_equal(rows.cpu().numpy(), want)
+    assert int(row_off[-1]) == want.shape[0]
+
+
+# ---- K2+K3 vs the reference's golden logits ----------------------------------------------------------
+@pytest.mark.parametrize("case", ["se_L100", "se_L150", "se_L300"])
+@pytest.mark.parametrize("semantics", ["packed", "padded"])
+def test_logits_match_reference_golden(gpu_model, case, semantics):
+    g = load_golden(case)
+    L = int(g["max_len"])
+    for prec in built_precisions(gpu_model):
+        logits, probs, labels = gpu_model.classify(g["seq"], g["off"], L, semantics=semantics,
+                                                   precision=prec, want_probs=True)
+        got = logits.cpu().numpy()
+        check_logits(got, g["logits_" + semantics], prec)
+        check_logits(got, g["logits_%s_f64" % semantics], prec)
+        assert np.array_equal(labels.cpu().numpy(), pairs.argmax_labels(got))
+        assert np.abs(probs.cpu().numpy() - softmax2(got.astype(np.float64))).max() < 1e-6
+
+
+def test_dropin_call_takes_reference_collate_outputs(gpu_model):
+    """model(PackedSequence) and model([B,T,4]) — what detect.py:685/687 hand to the model."""
+    from torch.nn.utils.rnn import pack_sequence
+    g = load_golden("se_L100")
+    reads = split_reads(g["seq"], g["off"])[:200]
+    xs = [torch.from_numpy(encoders.encode_read(r[:100])) for r in reads]
+    out = gpu_model(pack_sequence(xs, enforce_sorted=False))
+    assert out.shape == (200, 2) and out.is_cuda
+    check_logits(out.cpu().numpy(), g["logits_packed"][:200], "fp32")
+    x = torch.from_numpy(np.stack([encoders.encode_variable_len_read(r, 100) for r in reads]))
+    out = gpu_model(x)
+    check_logits(out.cpu().numpy(), g["logits_padded"][:200], "fp32")
+
+
+# ---- K3: argmax / pair combination: bit-exact ---------------------------------------------------------
+def test_pair_combine_matches_reference_golden(gpu_model):
+    g = load_golden("pe_L100")
+    l1 = torch.from_numpy(g["logits1"]).cuda()
+    l2 = torch.from_numpy(g["logits2"]).cuda()
+    for mode in pairs.MODES:
+        counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+        lab = gpu_model.pair_combine(l1, l2, mode, counts=counts).cpu().numpy()
+        assert np.array_equal(lab, g["labels_" + mode]), mode
+        assert np.array_equal(counts.cpu().numpy(), pairs.counts(lab))
+    with pytest.raises(ValueError):
+        gpu_model.pair_combine(l1, l2, "sometimes")
+
+
+def test_pairs_end_to_end_host_api(gpu_model):
+    g = load_golden("pe_L100")
+    for mode in pairs.MODES:
+        r = gpu_model.classify_pairs_host(g["r1_seq"], g["r1_off"], g["r2_seq"], g["r2_off"], 100,
+                                          mode=mode, want_logits=True)
+        check_logits(r["logits1"].numpy(), g["logits1"], "fp32")
+        check_logits(r["logits2"].numpy(), g["logits2"], "fp32")
+        want = pairs.pair_labels(r["logits1"].numpy(), r["logits2"].numpy(), mode)
+        assert np.array_equal(r["labels"].numpy(), want)
+        assert np.array_equal(r["counts"].numpy(), pairs.counts(want))
+        margin = np.minimum(np.abs(g["logits1"][:, 1] - g["logits1"][:, 0]),
+                            np.abs(g["logits2"][:, 1] - g["logits2"][:, 0]))
+        s = g["logits1"] + g["logits2"]
+        margin = np.minimum(margin, np.abs(s[:, 1] - s[:, 0]))
+        ok = margin > 1e-3
+        assert np.array_equal(r["labels"].numpy()[ok], g["labels_" + mode][ok])
+
+
+def test_ties_go_to_class0(gpu_model):
+    g = load_golden("ties")
+    l = torch.from_numpy(g["logits"]).cuda()
+    z = torch.zeros_like(l)
+    assert np.array_equal(gpu_model.pair_combine(l, z, "none").cpu().numpy(), g["labels"])
+    assert np.array_equal(gpu_model.pair_combine(l, l, "both").cpu().numpy(), g["labels"])
+
+
+# ---- seeded inputs vs the oracle ---------------------------------------------------------------------
+@pytest.mark.parametrize("semantics", ["packed", "padded"])
+def test_ragged_reads_match_oracle(gpu_model, numpy_oracle, semantics):
+    seq, off = synth.synth_reads(3000, 1, 260, 11, n_frac=0.02)
+    reads = synth.to_strings(seq, off)
+    ref = numpy_oracle.logits(reads, 200, semantics)
+    for prec in built_precisions(gpu_model):
+        got = gpu_model.classify(seq, off, 200, semantics=semantics, precision=prec)[0].cpu().numpy()
+        check_logits(got, ref, prec)
+
+
+def test_fixed_100bp_reads_match_torch_oracle(gpu_model, torch_oracle):
+    seq, off = synth.synth_reads_fixed(4096, 100, synth.SEED_BASE + 1)
+    reads = synth.to_strings(seq, off)
+    ref = torch_oracle.logits_packed(reads, 100)
+    for prec in built_precisions(gpu_model):
+        r = gpu_model.classify_host(seq, off, 100, precision=prec, want_probs=True)
+        d = check_logits(r["logits"].numpy(), ref, prec)
+        lab = r["labels"].numpy()
+        assert np.array_equal(lab, pairs.argmax_labels(r["logits"].numpy()))
+        assert np.array_equal(r["counts"].numpy(), pairs.counts(lab))
+        assert 0 < r["counts"][1] < 0.2 * 4096          # both classes exercised
+        print("precision %s: max|dlogit| = %.3e" % (prec, d))
+
+
+# ---- edge cases ----------------------------------------------------------------------------------------
+def test_empty_inputs_and_empty_reads(gpu_model, numpy_oracle):
+    r = gpu_model.classify_host(np.zeros(0, np.uint8), np.zeros(1, np.int64), 100)
+    assert r["labels"].numel() == 0 and r["counts"].tolist() == [0, 0, 0]
+    seq, off = encoders.flatten_reads(["ACGT", "", "GG"])
+    with pytest.raises(_lib.RdError):                   # torch pack_sequence raises too
+        gpu_model.classify_host(seq, off, 100, semantics="packed")
+    got = gpu_model.classify_host(seq, off, 50, semantics="padded")["logits"].numpy()
+    check_logits(got, numpy_oracle.logits(["ACGT", "", "GG"], 50, "padded"), "fp32")
+    with pytest.raises(ValueError):
+        gpu_model.classify_host(seq, off, 0)
+    with pytest.raises(ValueError):
+        gpu_model.classify_host(seq, off, _lib.RD_MAX_LEN + 1)
+
+
+def test_max_len_supported(gpu_model, numpy_oracle):
+    seq, off = synth.synth_reads(40, 3000, 4200, 5)
+    reads = synth.to_strings(seq, off)
+    got = gpu_model.classify(seq, off, _lib.RD_MAX_LEN)[0].cpu().numpy()
+    check_logits(got, numpy_oracle.logits(reads, _lib.RD_MAX_LEN, "packed"), "fp32")
+
+
+# ---- size-independent properties ------------------------------------------------------------------------
+def test_permutation_equivariance_is_bit_exact(gpu_model):
+    """Length bucketing reshuffles reads into tiles; a read's result must not depend on its
+    tile-mates: classify(perm(reads)) == perm(classify(reads)) bit for bit."""
+    seq, off = synth.synth_reads(20000, 40, 130, 3)
+    reads = np.array(synth.to_strings(seq, off), dtype=object)
+    rng = np.random.default_rng(0)
+    p = rng.permutation(len(reads))
+    seq2, off2 = encoders.flatten_reads(list(reads[p]))
+    for prec in built_precisions(gpu_model):
+        a = gpu_model.classify(seq, off, 100, precision=prec)[0].cpu().numpy()
+        b = gpu_model.classify(seq2, off2, 100, precision=prec)[0].cpu().numpy()
+        assert np.array_equal(a[p], b)
+
+
+def test_truncation_and_u_equals_t(gpu_model):
+    seq, off = synth.synth_reads(2000, 90, 160, 9)
+    reads = synth.to_strings(seq, off)
+    cut = [r[:100].replace("T", "U") for r in reads]
+    seq2, off2 = encoders.flatten_reads(cut)
+    a = gpu_model.classify(seq, off, 100)[0].cpu().numpy()
+    b = gpu_model.classify(seq2, off2, 100)[0].cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+def test_host_pipeline_chunks_equal_device_path(gpu_model):
+    """> 1 pipeline chunk (2 Mi reads each) of short reads; host API == device API, counts ==
+    histogram of labels."""
+    n = (1 << 21) + 4097
+    seq, off = synth.synth_reads(n, 4, 12, 21)
+    r = gpu_model.classify_host(seq, off, 16)
+    logits, _, labels = gpu_model.classify(seq, off, 16)
+    assert np.array_equal(r["logits"].numpy(), logits.cpu().numpy())
+    assert np.array_equal(r["labels"].numpy(), labels.cpu().numpy())
+    assert np.array_equal(r["counts"].numpy(), pairs.counts(r["labels"].numpy()))
+    assert int(r["counts"].sum()) == n
+
+
+def test_kernel_launch_counter_moves(gpu_model):
+    before = gpu_model.kernel_launches()
+    seq, off = synth.synth_reads_fixed(256, 50, 1)
+    gpu_model.classify(seq, off, 50)
+    assert gpu_model.kernel_launches() - before >= 6
