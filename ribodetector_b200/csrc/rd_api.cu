@@ -115,7 +115,7 @@ extern "C" int rd_create(int device,
     CK(cudaMalloc(&h->d_stage_counts, sizeof(int64_t) * 4));
     int rc = rd_build_reverse_lut(h, nullptr, 0);
     if (rc != RD_OK) return bail(rc);
-    rc = rd_tc_create(h, w_hh_f, tab_f.data());
+    rc = rd_tc_create(h, w_hh_f, w_ih_f, b_ih_f, b_hh_f);
     if (rc != RD_OK) return bail(rc);
     CK(cudaDeviceSynchronize());
 #undef CK

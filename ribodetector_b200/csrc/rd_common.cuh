@@ -103,5 +103,5 @@ int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_prob
 int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n, int mode,
                    int8_t* d_labels, int64_t* d_counts, cudaStream_t st);
 int rd_build_reverse_lut(rd_handle* h, const float* d_wout_full, cudaStream_t st);
-int rd_tc_create(rd_handle* h, const float* w_hh_f_host, const float* tab_f_host);
+int rd_tc_create(rd_handle* h, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh);
 void rd_tc_destroy(rd_handle* h);

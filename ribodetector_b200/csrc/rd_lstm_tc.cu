@@ -1,10 +1,569 @@
-// rd_lstm_tc.cu — K2 (RD_PREC_TC_EXACT / RD_PREC_TC_FAST): tcgen05 forward LSTM.  (placeholder
-// until the tensor-core kernel lands; fails loudly, never falls back)
+// rd_lstm_tc.cu — K2 on the 5th-generation tensor cores (RD_PREC_TC_FAST / RD_PREC_TC_EXACT).
+//
+// Replaces `self.rnn(x, None)` + `last_items` + `self.out` (model/model.py:33-36) for the forward
+// direction; the reverse direction enters through the logit LUT (rd_tail.cu).
+//
+// One persistent CTA per SM owns one tile of 128 reads at a time (TMEM lane = read).  Per step t
+//     Z[128, 512] = [h_{t-1} | onehot(x_t), 1] . [W_hh ; W_ih ; b]^T          (tcgen05.mma, kind::f16)
+// with  A = h_{t-1} (+ the 16-wide one-hot/bias chunk) resident in TENSOR MEMORY, written there by the
+//           activation warps with tcgen05.st (fp16; EXACT: fp16 hi + fp16 lo residual),
+//       B = the recurrent weights, staged ONCE per CTA into shared memory by the TMA bulk-copy
+//           engine (cp.async.bulk) in the K-major SWIZZLE_NONE canonical layout,
+//       D = fp32 accumulators in tensor memory, produced in 8 column chunks of 64 (= 16 hidden
+//           units x 4 gates, gate-interleaved so one tcgen05.ld.32x32b.x32 hands a thread i,f,g,o of
+//           8 units of its read) through a ring of NBUF chunk buffers.
+// Eight activation warps (4 lane quarters x 2 unit-group parities) drain the chunks: sigmoid/tanh,
+// cell update in fp32 registers, h_t back into the other A buffer.  One elected thread issues the
+// MMAs.  The recurrence is pipelined as a wavefront: chunk 0 of step t+1 accumulates K-chunk kc as
+// soon as the activation warps have published the 16 hidden units of K-chunk kc of step t
+// (h_ready[kc]), so the tensor pipe trails the activation pipe by one chunk instead of one step.
+//
+// FAST  : cta_group::1, one fp16 pass (9 MMAs of 128x64x16 per chunk), tanh.approx activations.
+// EXACT : cta_group::2 — a CTA pair shares the weights (each SM holds half of the N columns of
+//         W_hi and W_lo: 136 KB) and runs two tiles (M = 256) in lock step; three fp16 passes
+//         W_hi.h_hi + W_lo.h_hi + W_hi.h_lo (25 MMAs per chunk) with fp32 accumulation; ex2/rcp
+//         activations accurate to a few ulp.
+// See DESIGN.md for the layout tables and the roofline arithmetic.
+#include <cuda_fp16.h>
 #include "rd_common.cuh"
 
-int rd_tc_create(rd_handle*, const float*, const float*) { return RD_OK; }
-void rd_tc_destroy(rd_handle*) {}
-int rd_launch_lstm_tc(rd_handle* h, int64_t, int, int, float*, cudaStream_t) {
-    h->err = "tensor-core precision modes are not built in this library";
-    return RD_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = EPI_THREADS + 32;          // + the MMA / allocator warp
+constexpr int CHUNKS = 8;                             // column chunks per step
+constexpr int CHUNK_N = 64;                           // D columns per chunk
+constexpr int KG_H = 16;                              // 8-wide k-groups of h
+constexpr int KG_X = 2;                               // k-groups of the one-hot/bias chunk
+
+template <bool EXACT>
+struct Cfg {
+    static constexpr int CG = EXACT ? 2 : 1;                      // CTAs per MMA (cta_group)
+    static constexpr int NL = RD_G4 / CG;                         // weight rows resident per CTA
+    static constexpr int HI_BYTES = (KG_H + KG_X) * NL * 16;      // FAST 147456, EXACT 73728
+    static constexpr int LO_BYTES = EXACT ? KG_H * NL * 16 : 0;   // EXACT 65536
+    static constexpr int LBO = NL * 16;                           // bytes between k-groups
+    static constexpr int XCOL = EXACT ? 128 : 64;                 // A buffer: [h_hi 64 | h_lo 64 | x 8]
+    static constexpr int ACOLS = XCOL + 8;
+    static constexpr int NBUF = EXACT ? 2 : 4;                    // D chunk ring
+    static constexpr int DCOL0 = EXACT ? 320 : 256;
+    static constexpr int M = 128 * CG;
+    // shared memory carve-up (bytes)
+    static constexpr int OFF_LO = HI_BYTES;
+    static constexpr int OFF_WOUT = HI_BYTES + LO_BYTES;          // float [2][128]
+    static constexpr int OFF_PART = OFF_WOUT + 2 * RD_H * 4;      // float2 [2][128]
+    static constexpr int OFF_BAR = OFF_PART + 2 * RD_TILE * 8;    // mbarriers
+    static constexpr int N_BAR = 2 + CHUNKS + 2 * NBUF;
+    static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
+    static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c),
+                 "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE (layout verified by tools/tc_probe.cu)
+//   byte(n, k) = (k/8)*LBO + (n/8)*SBO + (n%8)*16 + (k%8)*2 ; fields are in 16-byte units
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor, kind::f16: D = f32 (bit 4), A = B = f16, both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int CG>
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if constexpr (CG == 1) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                         "r"(bar), "h"((uint16_t)3) : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- activations ----------------------------------------------------------------------------------
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_mufu(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_mufu(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool EXACT>
+__device__ __forceinline__ float act_sigmoid(float z) {
+    if constexpr (EXACT) return rcp_mufu(1.0f + ex2_mufu(-1.4426950408889634f * z));   // 1/(1+e^-z)
+    else return fmaf(tanh_mufu(0.5f * z), 0.5f, 0.5f);
+}
+template <bool EXACT>
+__device__ __forceinline__ float act_tanh(float z) {
+    if constexpr (EXACT) return fmaf(-2.0f, rcp_mufu(1.0f + ex2_mufu(2.8853900817779268f * z)), 1.0f);   // 1 - 2/(1+e^2z)
+    else return tanh_mufu(z);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// one-hot/bias chunk of a read at one step: k = [onehot4 (W_ih hi rows) | onehot4 (W_ih lo rows) | 1 | 1 | 0 x6]
+__device__ __forceinline__ void x_chunk(uint32_t code, uint32_t (&r)[8]) {
+    const uint32_t a = (code == 0u ? 0x00003C00u : 0u) | (code == 1u ? 0x3C000000u : 0u);
+    const uint32_t b = (code == 2u ? 0x00003C00u : 0u) | (code == 3u ? 0x3C000000u : 0u);
+    r[0] = a; r[1] = b; r[2] = a; r[3] = b; r[4] = 0x3C003C00u; r[5] = 0u; r[6] = 0u; r[7] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ splan,
+               const int32_t* __restrict__ perm, int L, int n_tiles,
+               const uint8_t* __restrict__ img_hi,     // [CG][HI_BYTES] weight images (rd_tc_create)
+               const uint8_t* __restrict__ img_lo,     // [CG][LO_BYTES]
+               const float* __restrict__ wout,         // [2][256]
+               const float* __restrict__ bout,         // [2]
+               const float* __restrict__ revlut,       // [RD_MAX_LEN][5][2]
+               float* __restrict__ logits) {
+    using C = Cfg<EXACT>;
+    constexpr int CG = C::CG;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_hi = s_base, s_lo = s_base + C::OFF_LO;
+    float* wout_s = reinterpret_cast<float*>(smem + C::OFF_WOUT);
+    float2* part_s = reinterpret_cast<float2*>(smem + C::OFF_PART);
+    const uint32_t bar_w = s_base + C::OFF_BAR;               // weights landed
+    const uint32_t bar_tile = bar_w + 8;                      // tile set up (x_0 written)      [leader]
+    const uint32_t bar_h = bar_w + 16;                        // h_ready[8]                     [leader]
+    const uint32_t bar_full = bar_h + 8 * CHUNKS;             // acc_full[NBUF]                 [each CTA]
+    const uint32_t bar_empty = bar_full + 8 * C::NBUF;        // acc_empty[NBUF]                [leader]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;      // a unit = one CTA (pair)
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_tile, EPI_WARPS * CG);
+        for (int i = 0; i < CHUNKS; ++i) mbar_init(bar_h + 8 * i, EPI_WARPS * CG);
+        for (int i = 0; i < C::NBUF; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, EPI_WARPS * CG);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // stage this CTA's weight image once: TMA bulk copies, completion on bar_w
+        mbar_expect_tx(bar_w, C::HI_BYTES + C::LO_BYTES);
+        const uint8_t* src_hi = img_hi + (size_t)rank * C::HI_BYTES;
+        for (int o = 0; o < C::HI_BYTES; o += 8192) bulk_g2s(s_hi + o, src_hi + o, 8192, bar_w);
+        if constexpr (EXACT) {
+            const uint8_t* src_lo = img_lo + (size_t)rank * C::LO_BYTES;
+            for (int o = 0; o < C::LO_BYTES; o += 8192) bulk_g2s(s_lo + o, src_lo + o, 8192, bar_w);
+        }
+    }
+    for (int i = tid; i < 2 * RD_H; i += TC_THREADS) wout_s[i] = wout[(i >> 7) * 2 * RD_H + (i & 127)];   // fwd half of W_out
+    if (warp == EPI_WARPS) {
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CG == 2) cluster_sync();        // peer's barriers are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == EPI_WARPS) {
+        // =============================== MMA issuer (leader CTA, one thread) ===============================
+        if (rank == 0 && lane == 0) {
+            mbar_wait(bar_w, 0);
+            // (the peer's half of the weights has landed before its activation warps first arrive on
+            //  bar_tile: they wait on their own bar_w first)
+            constexpr uint32_t idesc = make_idesc(C::M, CHUNK_N);
+            constexpr uint32_t NB = CHUNK_N / CG;             // weight rows per CTA per chunk
+            uint32_t hcnt = 0, it = 0;
+            for (int tile = unit * CG; tile < n_tiles; tile += n_units * CG, ++it) {
+                const int T = (int)PLAN_NFWD(splan[(int64_t)tile * RD_TILE]);
+                if constexpr (CG == 2) mbar_wait_cluster(bar_tile, it & 1); else mbar_wait(bar_tile, it & 1);
+                tc_fence_after();
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t abuf = tmem + (uint32_t)(((t + 1) & 1) * C::ACOLS);
+#pragma unroll
+                    for (int cc = 0; cc < CHUNKS; ++cc) {
+                        const int buf = cc % C::NBUF;
+                        const uint32_t eparity = ((cc / C::NBUF) & 1) ^ 1;
+                        if constexpr (CG == 2) mbar_wait_cluster(bar_empty + 8 * buf, eparity);
+                        else mbar_wait(bar_empty + 8 * buf, eparity);
+                        if (cc == 0 && t > 0) {
+                            if constexpr (CG == 2) mbar_wait_cluster(bar_h, hcnt & 1); else mbar_wait(bar_h, hcnt & 1);
+                        }
+                        tc_fence_after();
+                        const uint32_t d = tmem + (uint32_t)(C::DCOL0 + buf * CHUNK_N);
+                        const uint32_t boff = (uint32_t)(cc * NB * 16);          // chunk's rows inside a k-group
+                        // input projection + biases (hi and lo rows share the chunk): overwrites D
+                        mma_ts<CG>(d, abuf + C::XCOL, make_desc(s_hi + KG_H * C::LBO + boff, C::LBO, 128), idesc, 0u);
+                        if (t > 0) {
+#pragma unroll
+                            for (int kc = 0; kc < 8; ++kc) {
+                                if (cc == 0 && kc > 0) {
+                                    if constexpr (CG == 2) mbar_wait_cluster(bar_h + 8 * kc, hcnt & 1);
+                                    else mbar_wait(bar_h + 8 * kc, hcnt & 1);
+                                    tc_fence_after();
+                                }
+                                const uint64_t bhi = make_desc(s_hi + 2 * kc * C::LBO + boff, C::LBO, 128);
+                                mma_ts<CG>(d, abuf + 8 * kc, bhi, idesc, 1u);
+                                if constexpr (EXACT) {
+                                    const uint64_t blo = make_desc(s_lo + 2 * kc * C::LBO + boff, C::LBO, 128);
+                                    mma_ts<CG>(d, abuf + 8 * kc, blo, idesc, 1u);           // W_lo . h_hi
+                                    mma_ts<CG>(d, abuf + 64 + 8 * kc, bhi, idesc, 1u);      // W_hi . h_lo
+                                }
+                            }
+                        }
+                        mma_commit<CG>(bar_full + 8 * buf);
+                    }
+                    if (t > 0) ++hcnt;
+                }
+            }
+        }
+    } else {
+        // =============================== activation warps ===============================
+        const int q = warp & 3, par = warp >> 2;
+        const int row = q * 32 + lane;                                   // read slot inside the tile
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        mbar_wait(bar_w, 0);                                             // wout_s visible after __syncthreads; weights landed
+        uint32_t it = 0;
+        for (int tile0 = unit * CG; tile0 < n_tiles; tile0 += n_units * CG, ++it) {
+            const int tile = tile0 + (int)rank;
+            const int64_t slot = (int64_t)tile * RD_TILE + row;
+            const int T = (int)PLAN_NFWD(splan[(int64_t)tile0 * RD_TILE]);   // steps of the unit's longest read
+            const uint32_t myplan = tile < n_tiles ? splan[slot] : 0u;
+            const int nf = (int)PLAN_NFWD(myplan);
+            const uint8_t* cptr = codes + (int64_t)tile * L * RD_TILE + row;
+            const bool have_tile = tile < n_tiles;
+            float c[8][8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) c[g][u] = 0.f;
+            float p0 = 0.f, p1 = 0.f;
+            uint32_t code_next = 4u, code_next2 = 4u;
+            if (par == 0) {
+                const uint32_t code0 = (have_tile && T > 0) ? cptr[0] : 4u;
+                code_next = (have_tile && T > 1) ? cptr[RD_TILE] : 4u;
+                uint32_t xr[8];
+                x_chunk(code0, xr);
+                tmem_st8(tmem + (uint32_t)C::ACOLS + lane_off + C::XCOL, xr);     // x_0 -> A buffer 1
+                tc_wait_st();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_tile, 0); else mbar_arrive(bar_tile); }
+
+            for (int t = 0; t < T; ++t) {
+                if (par == 0) code_next2 = (have_tile && t + 2 < T) ? cptr[(int64_t)(t + 2) * RD_TILE] : 4u;
+                const bool active = t < nf;
+                const bool last = t == nf - 1;
+                const bool more = t + 1 < T;
+                const uint32_t awr = tmem + (uint32_t)((t & 1) * C::ACOLS) + lane_off;   // h_t goes to buffer t&1
+#pragma unroll
+                for (int cc = 0; cc < CHUNKS; ++cc) {
+                    const int buf = cc % C::NBUF;
+                    mbar_wait(bar_full + 8 * buf, (cc / C::NBUF) & 1);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(tmem + (uint32_t)(C::DCOL0 + buf * CHUNK_N + par * 32) + lane_off, v);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_empty + 8 * buf, 0); else mbar_arrive(bar_empty + 8 * buf); }
+
+                    float hv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float ig = act_sigmoid<EXACT>(__uint_as_float(v[u]));
+                        const float fg = act_sigmoid<EXACT>(__uint_as_float(v[8 + u]));
+                        const float gg = act_tanh<EXACT>(__uint_as_float(v[16 + u]));
+                        const float og = act_sigmoid<EXACT>(__uint_as_float(v[24 + u]));
+                        const float cn = fmaf(fg, c[cc][u], ig * gg);
+                        hv[u] = og * act_tanh<EXACT>(cn);
+                        if (active) c[cc][u] = cn;
+                    }
+                    if (last) {        // fused FC: this thread's 8 units of W_out[:, :H] . h_fwd   (model.py:36)
+                        const int u0 = (2 * cc + par) * 8;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            p0 = fmaf(wout_s[u0 + u], hv[u], p0);
+                            p1 = fmaf(wout_s[RD_H + u0 + u], hv[u], p1);
+                        }
+                    }
+                    if (more) {
+                        const uint32_t hcol = awr + (uint32_t)(4 * (2 * cc + par));
+                        if constexpr (EXACT) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __half2 h2 = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
+                                float2 back = __half22float2(h2);
+                                hi[j] = *reinterpret_cast<uint32_t*>(&h2);
+                                lo[j] = pack_h2(hv[2 * j] - back.x, hv[2 * j + 1] - back.y);
+                            }
+                            tmem_st4(hcol, hi[0], hi[1], hi[2], hi[3]);
+                            tmem_st4(hcol + 64, lo[0], lo[1], lo[2], lo[3]);
+                        } else {
+                            tmem_st4(hcol, pack_h2(hv[0], hv[1]), pack_h2(hv[2], hv[3]), pack_h2(hv[4], hv[5]),
+                                     pack_h2(hv[6], hv[7]));
+                        }
+                        if (cc == 0 && par == 0) {
+                            uint32_t xr[8];
+                            x_chunk(code_next, xr);
+                            tmem_st8(awr + C::XCOL, xr);                  // x_{t+1} rides with K-chunk 0
+                        }
+                        tc_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_h + 8 * cc, 0); else mbar_arrive(bar_h + 8 * cc); }
+                    }
+                }
+                code_next = code_next2;
+            }
+
+            // tile tail: combine the two unit-group parities, add the reverse-direction LUT and bias
+            part_s[par * RD_TILE + row] = make_float2(p0, p1);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            if (par == 0 && have_tile) {
+                const int32_t rd = perm[slot];
+                if (rd >= 0) {
+                    const float2 a = part_s[row], b = part_s[RD_TILE + row];
+                    const float* lut = revlut + ((int64_t)PLAN_KREV(myplan) * 5 + PLAN_CREV(myplan)) * 2;
+                    float l0 = a.x + b.x + lut[0] + bout[0];
+                    float l1 = a.y + b.y + lut[1] + bout[1];
+                    if (PLAN_INVALID(myplan)) { l0 = __int_as_float(0x7fc00000); l1 = l0; }
+                    *reinterpret_cast<float2*>(logits + (int64_t)rd * 2) = make_float2(l0, l1);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        }
+    }
+
+    // teardown: nobody leaves while the pair still references this CTA's memories
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CG == 2) cluster_sync();
+    if (warp == EPI_WARPS) {
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---- host side: weight images ----------------------------------------------------------------------
+// D column n  <->  hidden unit / gate:  n = 32*j + 8*gate + u8  with unit = 8*j + u8, gate in (i,f,g,o)
+inline int col_to_row(int n) { return ((n % 32) / 8) * RD_H + (n / 32) * 8 + (n % 8); }
+
+// image[rank][kg][n_local][8] halfs; chunk cc of the MMA takes rows cc*NB .. cc*NB+NB-1 of each rank,
+// which are D columns cc*64 + rank*NB + i  (cta_group::2: each CTA supplies half of the N columns).
+void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh, int cg,
+                  std::vector<__half>& hi, std::vector<__half>& lo, bool exact) {
+    const int NL = RD_G4 / cg, NB = CHUNK_N / cg;
+    hi.assign((size_t)cg * (KG_H + KG_X) * NL * 8, __float2half(0.f));
+    lo.assign(exact ? (size_t)cg * KG_H * NL * 8 : 0, __float2half(0.f));
+    for (int rank = 0; rank < cg; ++rank)
+        for (int nl = 0; nl < NL; ++nl) {
+            const int cc = nl / NB, i = nl % NB;
+            const int n = cc * CHUNK_N + rank * NB + i;
+            const int row = col_to_row(n);
+            for (int k = 0; k < RD_H; ++k) {
+                const float w = w_hh[row * RD_H + k];
+                const __half whi = __float2half_rn(w);
+                const size_t at = (((size_t)rank * (KG_H + KG_X) + k / 8) * NL + nl) * 8 + k % 8;
+                hi[at] = whi;
+                if (exact) {
+                    const size_t al = (((size_t)rank * KG_H + k / 8) * NL + nl) * 8 + k % 8;
+                    lo[al] = __float2half_rn(w - __half2float(whi));
+                }
+            }
+            // x chunk: k = 0..3 W_ih hi, 4..7 W_ih lo, 8 bias hi, 9 bias lo
+            const float bias = b_ih[row] + b_hh[row];
+            for (int cdx = 0; cdx < 4; ++cdx) {
+                const float w = w_ih[row * 4 + cdx];
+                const __half whi = __float2half_rn(w);
+                const size_t a0 = (((size_t)rank * (KG_H + KG_X) + KG_H) * NL + nl) * 8;
+                hi[a0 + cdx] = whi;
+                hi[a0 + 4 + cdx] = __float2half_rn(w - __half2float(whi));
+            }
+            const __half bhi = __float2half_rn(bias);
+            const size_t a1 = (((size_t)rank * (KG_H + KG_X) + KG_H + 1) * NL + nl) * 8;
+            hi[a1 + 0] = bhi;
+            hi[a1 + 1] = __float2half_rn(bias - __half2float(bhi));
+        }
+}
+
+}  // namespace
+
+struct rd_tc_state {
+    uint8_t* d_img_fast = nullptr;      // [1][147456]
+    uint8_t* d_img_hi = nullptr;        // [2][73728]
+    uint8_t* d_img_lo = nullptr;        // [2][65536]
+    bool attr_fast = false, attr_exact = false;
+};
+
+int rd_tc_create(rd_handle* h, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh) {
+    rd_tc_state* s = new (std::nothrow) rd_tc_state();
+    if (!s) { h->err = "rd_tc_create: out of host memory"; return RD_ERR_NOMEM; }
+    h->tc = s;
+    std::vector<__half> hi, lo;
+    build_images(w_hh, w_ih, b_ih, b_hh, 1, hi, lo, false);
+    RD_CUDA(h, cudaMalloc(&s->d_img_fast, hi.size() * sizeof(__half)));
+    RD_CUDA(h, cudaMemcpy(s->d_img_fast, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    build_images(w_hh, w_ih, b_ih, b_hh, 2, hi, lo, true);
+    RD_CUDA(h, cudaMalloc(&s->d_img_hi, hi.size() * sizeof(__half)));
+    RD_CUDA(h, cudaMalloc(&s->d_img_lo, lo.size() * sizeof(__half)));
+    RD_CUDA(h, cudaMemcpy(s->d_img_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    RD_CUDA(h, cudaMemcpy(s->d_img_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return RD_OK;
+}
+
+void rd_tc_destroy(rd_handle* h) {
+    if (!h->tc) return;
+    cudaFree(h->tc->d_img_fast); cudaFree(h->tc->d_img_hi); cudaFree(h->tc->d_img_lo);
+    delete h->tc;
+    h->tc = nullptr;
+}
+
+int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float* d_logits, cudaStream_t st) {
+    if (n_tiles == 0) return RD_OK;
+    rd_tc_state* s = h->tc;
+    if (!s) { h->err = "tensor-core state missing"; return RD_ERR_UNSUPPORTED; }
+    if (precision == RD_PREC_TC_FAST) {
+        using C = Cfg<false>;
+        if (!s->attr_fast) {
+            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            s->attr_fast = true;
+        }
+        int grid = (int)(n_tiles < h->sm_count ? n_tiles : h->sm_count);
+        lstm_tc_kernel<false><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(
+            h->d_codes, h->d_splan, h->d_perm, L, (int)n_tiles, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
+            h->d_revlut, d_logits);
+    } else {
+        using C = Cfg<true>;
+        if (!s->attr_exact) {
+            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            s->attr_exact = true;
+        }
+        int pairs = (int)((n_tiles + 1) / 2);
+        int max_pairs = h->sm_count / 2;
+        int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const uint8_t* codes = h->d_codes; const uint32_t* splan = h->d_splan; const int32_t* perm = h->d_perm;
+        int nt = (int)n_tiles;
+        const uint8_t* ihi = s->d_img_hi; const uint8_t* ilo = s->d_img_lo;
+        const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
+        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true>, codes, splan, perm, L, nt, ihi, ilo, wout, bout, lut,
+                                      d_logits));
+    }
+    h->launches += 1;
+    RD_CUDA(h, cudaGetLastError());
+    return RD_OK;
 }
