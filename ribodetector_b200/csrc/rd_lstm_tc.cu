@@ -27,34 +27,49 @@
 #include <cuda_fp16.h>
 #include "rd_common.cuh"
 
+#ifdef RD_TC_PROFILE
+__device__ unsigned long long g_tc_prof[16];
+#define PROF_DECL(x) long long x = 0
+#define PROF_T0() const long long _p0 = clock64()
+#define PROF_ADD(x) x += clock64() - _p0
+#else
+#define PROF_DECL(x)
+#define PROF_T0()
+#define PROF_ADD(x)
+#endif
+
 namespace {
 
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = EPI_THREADS + 32;          // + the MMA / allocator warp
-constexpr int CHUNKS = 8;                             // column chunks per step
-constexpr int CHUNK_N = 64;                           // D columns per chunk
+constexpr int KCHUNKS = 8;                            // K-chunks of h (16 hidden units each) per step
+constexpr int MMA_N = 128;                            // D columns per MMA chunk = 32 hidden units x 4 gates
+constexpr int MMA_CHUNKS = RD_G4 / MMA_N;             // 4 per step
+constexpr int NBUF = 2;                               // D chunk ring (2 x 128 columns)
 constexpr int KG_H = 16;                              // 8-wide k-groups of h
 constexpr int KG_X = 2;                               // k-groups of the one-hot/bias chunk
+constexpr int X_BYTES = 2 * RD_TILE * 16;             // one x buffer: [2 k-groups][128 rows][16 B]
 
 template <bool EXACT>
 struct Cfg {
     static constexpr int CG = EXACT ? 2 : 1;                      // CTAs per MMA (cta_group)
     static constexpr int NL = RD_G4 / CG;                         // weight rows resident per CTA
+    static constexpr int NB = MMA_N / CG;                         // weight rows per CTA per MMA chunk
     static constexpr int HI_BYTES = (KG_H + KG_X) * NL * 16;      // FAST 147456, EXACT 73728
     static constexpr int LO_BYTES = EXACT ? KG_H * NL * 16 : 0;   // EXACT 65536
     static constexpr int LBO = NL * 16;                           // bytes between k-groups
-    static constexpr int XCOL = EXACT ? 128 : 64;                 // A buffer: [h_hi 64 | h_lo 64 | x 8]
-    static constexpr int ACOLS = XCOL + 8;
-    static constexpr int NBUF = EXACT ? 2 : 4;                    // D chunk ring
-    static constexpr int DCOL0 = EXACT ? 320 : 256;
+    // tensor memory: A buffer s at column s*ACOLS = [h_hi 64 | h_lo 64 (EXACT)]; D ring at DCOL0
+    static constexpr int ACOLS = EXACT ? 128 : 64;
+    static constexpr int DCOL0 = 256;
     static constexpr int M = 128 * CG;
     // shared memory carve-up (bytes)
     static constexpr int OFF_LO = HI_BYTES;
-    static constexpr int OFF_WOUT = HI_BYTES + LO_BYTES;          // float [2][128]
+    static constexpr int OFF_X = HI_BYTES + LO_BYTES;             // 2 x X_BYTES one-hot/bias A operand
+    static constexpr int OFF_WOUT = OFF_X + 2 * X_BYTES;          // float [2][128]
     static constexpr int OFF_PART = OFF_WOUT + 2 * RD_H * 4;      // float2 [2][128]
     static constexpr int OFF_BAR = OFF_PART + 2 * RD_TILE * 8;    // mbarriers
-    static constexpr int N_BAR = 2 + CHUNKS + 2 * NBUF;
+    static constexpr int N_BAR = 2 + KCHUNKS + 2 * NBUF;
     static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
 };
@@ -74,11 +89,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // barrier with remote arrivals
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
@@ -86,12 +101,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `cta` of the cluster
+// Arrive on the barrier at the same offset in CTA `cta` of the cluster.  RELAXED on purpose: a
+// release at cluster scope costs MEMBAR.ALL.GPU + CCTL.IVALL per arrive (measured: ~2500 cycles per
+// LSTM step).  What the arrive publishes never travels through memory the waiter reads: it is this
+// SM's own tensor memory (completed by tcgen05.wait::st, ordered by tcgen05.fence::before_thread_sync)
+// and this SM's own shared memory (made visible to the async proxy by fence.proxy.async), both
+// consumed later by this SM's own tensor core when the leader issues the cta_group::2 MMA.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar), "r"(cta) : "memory");
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -150,6 +170,18 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
     }
 }
 template <int CG>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if constexpr (CG == 1) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+template <int CG>
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     if constexpr (CG == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -157,6 +189,11 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
                          "r"(bar), "h"((uint16_t)3) : "memory");
     }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -183,27 +220,54 @@ __device__ __forceinline__ float rcp_mufu(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// One LSTM cell update from the four gate pre-activations of one hidden unit.  The weight images
+// carry a per-gate scale (rd_tc_create) so that the values read from tensor memory are directly
+// the arguments the activation hardware wants:
+//   FAST : zi,zf,zo = z/2, zg = z          sigmoid(z) = 0.5 tanh(z/2) + 0.5     (MUFU.TANH, 5 per unit)
+//   EXACT: zi,zf,zo = -z log2e, zg = -2 z log2e, so A = 2^zi = e^-z etc. and
+//            c' = f c + i g = (c (1+A)(1+B) + (1-B)(1+F)) / ((1+F)(1+A)(1+B))       A = e^-zi, B = e^-2zg, F = e^-zf
+//            h  = o tanh(c') = (1-D) / ((1+O)(1+D))                                  O = e^-zo, D = e^-2c'
+//          i.e. 5 MUFU.EX2 + 2 MUFU.RCP per unit (instead of 5 + 5), each within a few ulp.  Exponent
+//          arguments are clamped at e^28 (sigmoid/tanh are saturated to fp32 precision long before)
+//          so the triple product stays finite.
+constexpr float EXACT_SCALE_IFO = -1.4426950408889634f;     // -log2(e)
+constexpr float EXACT_SCALE_G = -2.8853900817779268f;       // -2 log2(e)
+constexpr float EXACT_CLAMP = 40.395461f;                   // 28 log2(e)
 template <bool EXACT>
-__device__ __forceinline__ float act_sigmoid(float z) {
-    if constexpr (EXACT) return rcp_mufu(1.0f + ex2_mufu(-1.4426950408889634f * z));   // 1/(1+e^-z)
-    else return fmaf(tanh_mufu(0.5f * z), 0.5f, 0.5f);
-}
-template <bool EXACT>
-__device__ __forceinline__ float act_tanh(float z) {
-    if constexpr (EXACT) return fmaf(-2.0f, rcp_mufu(1.0f + ex2_mufu(2.8853900817779268f * z)), 1.0f);   // 1 - 2/(1+e^2z)
-    else return tanh_mufu(z);
+__device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo, float c_old, float& c_new, float& h_new) {
+    if constexpr (EXACT) {
+        const float A = ex2_mufu(fminf(zi, EXACT_CLAMP));
+        const float B = ex2_mufu(fminf(zg, EXACT_CLAMP));
+        const float F = ex2_mufu(fminf(zf, EXACT_CLAMP));
+        const float P = (1.0f + A) * (1.0f + B);
+        const float Q = 1.0f + F;
+        const float num = fmaf(c_old, P, (1.0f - B) * Q);
+        c_new = num * rcp_mufu(Q * P);
+        const float O = ex2_mufu(fminf(zo, EXACT_CLAMP));
+        const float D = ex2_mufu(fminf(EXACT_SCALE_G * c_new, EXACT_CLAMP));
+        h_new = (1.0f - D) * rcp_mufu((1.0f + O) * (1.0f + D));
+    } else {
+        const float ig = fmaf(tanh_mufu(zi), 0.5f, 0.5f);
+        const float fg = fmaf(tanh_mufu(zf), 0.5f, 0.5f);
+        const float gg = tanh_mufu(zg);
+        const float og = fmaf(tanh_mufu(zo), 0.5f, 0.5f);
+        c_new = fmaf(fg, c_old, ig * gg);
+        h_new = og * tanh_mufu(c_new);
+    }
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// one-hot/bias chunk of a read at one step: k = [onehot4 (W_ih hi rows) | onehot4 (W_ih lo rows) | 1 | 1 | 0 x6]
-__device__ __forceinline__ void x_chunk(uint32_t code, uint32_t (&r)[8]) {
+// one-hot/bias chunk of a read at one step, k = [onehot4 (W_ih hi rows) | onehot4 (W_ih lo rows) | 1 | 1 | 0 x6]:
+// k-group 0 (this 16-byte row) changes per step, k-group 1 = {1, 1, 0...} is written once per kernel.
+__device__ __forceinline__ void st_x_row(uint32_t saddr, uint32_t code) {
     const uint32_t a = (code == 0u ? 0x00003C00u : 0u) | (code == 1u ? 0x3C000000u : 0u);
     const uint32_t b = (code == 2u ? 0x00003C00u : 0u) | (code == 3u ? 0x3C000000u : 0u);
-    r[0] = a; r[1] = b; r[2] = a; r[3] = b; r[4] = 0x3C003C00u; r[5] = 0u; r[6] = 0u; r[7] = 0u;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
 template <bool EXACT>
@@ -220,14 +284,14 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
     constexpr int CG = C::CG;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_hi = s_base, s_lo = s_base + C::OFF_LO;
+    const uint32_t s_hi = s_base, s_lo = s_base + C::OFF_LO, s_x = s_base + C::OFF_X;
     float* wout_s = reinterpret_cast<float*>(smem + C::OFF_WOUT);
     float2* part_s = reinterpret_cast<float2*>(smem + C::OFF_PART);
     const uint32_t bar_w = s_base + C::OFF_BAR;               // weights landed
     const uint32_t bar_tile = bar_w + 8;                      // tile set up (x_0 written)      [leader]
     const uint32_t bar_h = bar_w + 16;                        // h_ready[8]                     [leader]
-    const uint32_t bar_full = bar_h + 8 * CHUNKS;             // acc_full[NBUF]                 [each CTA]
-    const uint32_t bar_empty = bar_full + 8 * C::NBUF;        // acc_empty[NBUF]                [leader]
+    const uint32_t bar_full = bar_h + 8 * KCHUNKS;            // acc_full[NBUF]                 [each CTA]
+    const uint32_t bar_empty = bar_full + 8 * NBUF;           // acc_empty[NBUF]                [leader]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -237,8 +301,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_tile, EPI_WARPS * CG);
-        for (int i = 0; i < CHUNKS; ++i) mbar_init(bar_h + 8 * i, EPI_WARPS * CG);
-        for (int i = 0; i < C::NBUF; ++i) {
+        for (int i = 0; i < KCHUNKS; ++i) mbar_init(bar_h + 8 * i, EPI_WARPS * CG);
+        for (int i = 0; i < NBUF; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, EPI_WARPS * CG);
         }
@@ -253,6 +317,11 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
         }
     }
     for (int i = tid; i < 2 * RD_H; i += TC_THREADS) wout_s[i] = wout[(i >> 7) * 2 * RD_H + (i & 127)];   // fwd half of W_out
+    if (tid < 2 * RD_TILE) {      // constant k-group 1 of both x buffers: k8 = k9 = 1.0 (bias hi / lo rows), rest 0
+        const uint32_t a = s_x + (uint32_t)((tid >> 7) * X_BYTES + RD_TILE * 16 + (tid & 127) * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(a), "r"(0x3C003C00u), "r"(0u) : "memory");
+    }
+    fence_async_smem();
     if (warp == EPI_WARPS) {
         if constexpr (CG == 1) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -269,72 +338,108 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
     const uint32_t tmem = *tmem_slot;
 
     if (warp == EPI_WARPS) {
-        // =============================== MMA issuer (leader CTA, one thread) ===============================
-        if (rank == 0 && lane == 0) {
+        // ============ MMA issuer (leader CTA; warp-uniform control flow, one elected lane issues) ============
+        if (rank == 0) {
+            const bool elected = elect_one();
             mbar_wait(bar_w, 0);
             // (the peer's half of the weights has landed before its activation warps first arrive on
             //  bar_tile: they wait on their own bar_w first)
-            constexpr uint32_t idesc = make_idesc(C::M, CHUNK_N);
-            constexpr uint32_t NB = CHUNK_N / CG;             // weight rows per CTA per chunk
+            constexpr uint32_t idesc = make_idesc(C::M, MMA_N);
             uint32_t hcnt = 0, it = 0;
+            PROF_DECL(pw_empty); PROF_DECL(pw_h); PROF_DECL(pw_tile); PROF_DECL(pw_chunk); PROF_DECL(p_chunk0);
+#ifdef RD_TC_PROFILE
+            const long long p_begin = clock64();
+#endif
             for (int tile = unit * CG; tile < n_tiles; tile += n_units * CG, ++it) {
                 const int T = (int)PLAN_NFWD(splan[(int64_t)tile * RD_TILE]);
+                { PROF_T0();
                 if constexpr (CG == 2) mbar_wait_cluster(bar_tile, it & 1); else mbar_wait(bar_tile, it & 1);
+                PROF_ADD(pw_tile); }
                 tc_fence_after();
                 for (int t = 0; t < T; ++t) {
-                    const uint32_t abuf = tmem + (uint32_t)(((t + 1) & 1) * C::ACOLS);
+                    const uint32_t rd = (uint32_t)((t + 1) & 1);                   // operand buffer written during step t-1
+                    const uint32_t abuf = tmem + rd * C::ACOLS;
+                    const uint64_t xdesc = make_desc(s_x + rd * X_BYTES, RD_TILE * 16, 128);
 #pragma unroll
-                    for (int cc = 0; cc < CHUNKS; ++cc) {
-                        const int buf = cc % C::NBUF;
-                        const uint32_t eparity = ((cc / C::NBUF) & 1) ^ 1;
+                    for (int mc = 0; mc < MMA_CHUNKS; ++mc) {
+                        const int buf = mc & 1;
+                        const uint32_t eparity = ((mc >> 1) & 1) ^ 1;
+                        { PROF_T0();
                         if constexpr (CG == 2) mbar_wait_cluster(bar_empty + 8 * buf, eparity);
                         else mbar_wait(bar_empty + 8 * buf, eparity);
-                        if (cc == 0 && t > 0) {
+                        PROF_ADD(pw_empty); }
+                        if (mc == 0 && t > 0) {
+                            PROF_T0();
                             if constexpr (CG == 2) mbar_wait_cluster(bar_h, hcnt & 1); else mbar_wait(bar_h, hcnt & 1);
+                            PROF_ADD(pw_h);
                         }
                         tc_fence_after();
-                        const uint32_t d = tmem + (uint32_t)(C::DCOL0 + buf * CHUNK_N);
-                        const uint32_t boff = (uint32_t)(cc * NB * 16);          // chunk's rows inside a k-group
-                        // input projection + biases (hi and lo rows share the chunk): overwrites D
-                        mma_ts<CG>(d, abuf + C::XCOL, make_desc(s_hi + KG_H * C::LBO + boff, C::LBO, 128), idesc, 0u);
+#ifdef RD_TC_PROFILE
+                        if (mc == 2) p_chunk0 = clock64();
+#endif
+                        const uint32_t d = tmem + (uint32_t)(C::DCOL0 + buf * MMA_N);
+                        const uint32_t boff = (uint32_t)(mc * C::NB * 16);         // chunk's rows inside a k-group
+                        // input projection + biases (A from shared memory): overwrites D
+                        if (elected) mma_ss<CG>(d, xdesc, make_desc(s_hi + KG_H * C::LBO + boff, C::LBO, 128), idesc, 0u);
                         if (t > 0) {
 #pragma unroll
-                            for (int kc = 0; kc < 8; ++kc) {
-                                if (cc == 0 && kc > 0) {
+                            for (int kc = 0; kc < KCHUNKS; ++kc) {
+                                if (mc == 0 && kc > 0) {
+                                    PROF_T0();
                                     if constexpr (CG == 2) mbar_wait_cluster(bar_h + 8 * kc, hcnt & 1);
                                     else mbar_wait(bar_h + 8 * kc, hcnt & 1);
                                     tc_fence_after();
+                                    PROF_ADD(pw_h);
                                 }
-                                const uint64_t bhi = make_desc(s_hi + 2 * kc * C::LBO + boff, C::LBO, 128);
-                                mma_ts<CG>(d, abuf + 8 * kc, bhi, idesc, 1u);
-                                if constexpr (EXACT) {
-                                    const uint64_t blo = make_desc(s_lo + 2 * kc * C::LBO + boff, C::LBO, 128);
-                                    mma_ts<CG>(d, abuf + 8 * kc, blo, idesc, 1u);           // W_lo . h_hi
-                                    mma_ts<CG>(d, abuf + 64 + 8 * kc, bhi, idesc, 1u);      // W_hi . h_lo
+                                if (elected) {
+                                    const uint64_t bhi = make_desc(s_hi + 2 * kc * C::LBO + boff, C::LBO, 128);
+                                    mma_ts<CG>(d, abuf + 8 * kc, bhi, idesc, 1u);
+                                    if constexpr (EXACT) {
+                                        const uint64_t blo = make_desc(s_lo + 2 * kc * C::LBO + boff, C::LBO, 128);
+                                        mma_ts<CG>(d, abuf + 8 * kc, blo, idesc, 1u);           // W_lo . h_hi
+                                        mma_ts<CG>(d, abuf + 64 + 8 * kc, bhi, idesc, 1u);      // W_hi . h_lo
+                                    }
                                 }
                             }
                         }
-                        mma_commit<CG>(bar_full + 8 * buf);
+                        if (elected) mma_commit<CG>(bar_full + 8 * buf);
+                        __syncwarp();
+#ifdef RD_TC_PROFILE
+                        if (mc == 2 && t > 0) {      // time from the chunk's first issue to its completion (perturbs the pipeline)
+                            mbar_wait(bar_full + 8 * buf, (mc >> 1) & 1);
+                            pw_chunk += clock64() - p_chunk0;
+                        }
+#endif
                     }
                     if (t > 0) ++hcnt;
                 }
             }
+#ifdef RD_TC_PROFILE
+            if (blockIdx.x == 0 && elected) {
+                g_tc_prof[0] = clock64() - p_begin; g_tc_prof[1] = pw_empty; g_tc_prof[2] = pw_h; g_tc_prof[3] = pw_tile; g_tc_prof[15] = pw_chunk;
+            }
+#endif
         }
     } else {
         // =============================== activation warps ===============================
         const int q = warp & 3, par = warp >> 2;
         const int row = q * 32 + lane;                                   // read slot inside the tile
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        mbar_wait(bar_w, 0);                                             // wout_s visible after __syncthreads; weights landed
+        const uint32_t x_row = s_x + (uint32_t)(row * 16);               // this read's k-group-0 row in x buffer 0
+        mbar_wait(bar_w, 0);                                             // this CTA's weights have landed
         uint32_t it = 0;
+        PROF_DECL(pe_full); PROF_DECL(pe_ld); PROF_DECL(pe_st); PROF_DECL(pe_full0);
+#ifdef RD_TC_PROFILE
+        const long long pe_begin = clock64();
+#endif
         for (int tile0 = unit * CG; tile0 < n_tiles; tile0 += n_units * CG, ++it) {
             const int tile = tile0 + (int)rank;
             const int64_t slot = (int64_t)tile * RD_TILE + row;
             const int T = (int)PLAN_NFWD(splan[(int64_t)tile0 * RD_TILE]);   // steps of the unit's longest read
-            const uint32_t myplan = tile < n_tiles ? splan[slot] : 0u;
+            const bool have_tile = tile < n_tiles;
+            const uint32_t myplan = have_tile ? splan[slot] : 0u;
             const int nf = (int)PLAN_NFWD(myplan);
             const uint8_t* cptr = codes + (int64_t)tile * L * RD_TILE + row;
-            const bool have_tile = tile < n_tiles;
             float c[8][8];
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -345,10 +450,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             if (par == 0) {
                 const uint32_t code0 = (have_tile && T > 0) ? cptr[0] : 4u;
                 code_next = (have_tile && T > 1) ? cptr[RD_TILE] : 4u;
-                uint32_t xr[8];
-                x_chunk(code0, xr);
-                tmem_st8(tmem + (uint32_t)C::ACOLS + lane_off + C::XCOL, xr);     // x_0 -> A buffer 1
-                tc_wait_st();
+                st_x_row(x_row + X_BYTES, code0);                        // x_0 -> operand buffer 1
+                fence_async_smem();
             }
             tc_fence_before();
             __syncwarp();
@@ -359,28 +462,36 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                 const bool active = t < nf;
                 const bool last = t == nf - 1;
                 const bool more = t + 1 < T;
-                const uint32_t awr = tmem + (uint32_t)((t & 1) * C::ACOLS) + lane_off;   // h_t goes to buffer t&1
+                const uint32_t wr = (uint32_t)(t & 1);                                   // h_t, x_{t+1} go to buffer t&1
+                const uint32_t awr = tmem + wr * C::ACOLS + lane_off;
 #pragma unroll
-                for (int cc = 0; cc < CHUNKS; ++cc) {
-                    const int buf = cc % C::NBUF;
-                    mbar_wait(bar_full + 8 * buf, (cc / C::NBUF) & 1);
+                for (int cc = 0; cc < KCHUNKS; ++cc) {
+                    const int mc = cc >> 1, buf = mc & 1;
+                    { PROF_T0();
+                    if ((cc & 1) == 0) mbar_wait(bar_full + 8 * buf, (mc >> 1) & 1);
+                    PROF_ADD(pe_full);
+#ifdef RD_TC_PROFILE
+                    if (mc == 0) pe_full0 += clock64() - _p0;
+#endif
+                    }
                     tc_fence_after();
                     uint32_t v[32];
-                    tmem_ld32(tmem + (uint32_t)(C::DCOL0 + buf * CHUNK_N + par * 32) + lane_off, v);
+                    { PROF_T0();
+                    tmem_ld32(tmem + (uint32_t)(C::DCOL0 + buf * MMA_N + (cc & 1) * 64 + par * 32) + lane_off, v);
                     tc_wait_ld();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_empty + 8 * buf, 0); else mbar_arrive(bar_empty + 8 * buf); }
+                    PROF_ADD(pe_ld); }
+                    if (cc & 1) {                                        // this warp has drained its part of the D buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_empty + 8 * buf, 0); else mbar_arrive(bar_empty + 8 * buf); }
+                    }
 
                     float hv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const float ig = act_sigmoid<EXACT>(__uint_as_float(v[u]));
-                        const float fg = act_sigmoid<EXACT>(__uint_as_float(v[8 + u]));
-                        const float gg = act_tanh<EXACT>(__uint_as_float(v[16 + u]));
-                        const float og = act_sigmoid<EXACT>(__uint_as_float(v[24 + u]));
-                        const float cn = fmaf(fg, c[cc][u], ig * gg);
-                        hv[u] = og * act_tanh<EXACT>(cn);
+                        float cn;
+                        lstm_cell<EXACT>(__uint_as_float(v[u]), __uint_as_float(v[8 + u]), __uint_as_float(v[16 + u]),
+                                         __uint_as_float(v[24 + u]), c[cc][u], cn, hv[u]);
                         if (active) c[cc][u] = cn;
                     }
                     if (last) {        // fused FC: this thread's 8 units of W_out[:, :H] . h_fwd   (model.py:36)
@@ -408,15 +519,16 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                             tmem_st4(hcol, pack_h2(hv[0], hv[1]), pack_h2(hv[2], hv[3]), pack_h2(hv[4], hv[5]),
                                      pack_h2(hv[6], hv[7]));
                         }
-                        if (cc == 0 && par == 0) {
-                            uint32_t xr[8];
-                            x_chunk(code_next, xr);
-                            tmem_st8(awr + C::XCOL, xr);                  // x_{t+1} rides with K-chunk 0
+                        if (cc == 0 && par == 0) {                        // x_{t+1} rides with K-chunk 0
+                            st_x_row(x_row + wr * X_BYTES, code_next);
+                            fence_async_smem();
                         }
+                        { PROF_T0();
                         tc_wait_st();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_h + 8 * cc, 0); else mbar_arrive(bar_h + 8 * cc); }
+                        PROF_ADD(pe_st); }
                     }
                 }
                 code_next = code_next2;
@@ -438,6 +550,12 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         }
+#ifdef RD_TC_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {
+            unsigned long long* o = g_tc_prof + (warp == 5 ? 10 : 4);
+            o[0] = clock64() - pe_begin; o[1] = pe_full; o[2] = pe_ld; o[3] = pe_st; o[4] = pe_full0;
+        }
+#endif
     }
 
     // teardown: nobody leaves while the pair still references this CTA's memories
@@ -445,6 +563,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
     __syncthreads();
     if constexpr (CG == 2) cluster_sync();
     if (warp == EPI_WARPS) {
+        __syncwarp();
         if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
@@ -454,20 +573,23 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
 // D column n  <->  hidden unit / gate:  n = 32*j + 8*gate + u8  with unit = 8*j + u8, gate in (i,f,g,o)
 inline int col_to_row(int n) { return ((n % 32) / 8) * RD_H + (n / 32) * 8 + (n % 8); }
 
-// image[rank][kg][n_local][8] halfs; chunk cc of the MMA takes rows cc*NB .. cc*NB+NB-1 of each rank,
-// which are D columns cc*64 + rank*NB + i  (cta_group::2: each CTA supplies half of the N columns).
+// image[rank][kg][n_local][8] halfs; MMA chunk cc takes rows cc*NB .. cc*NB+NB-1 of each rank,
+// which are D columns cc*128 + rank*NB + i  (cta_group::2: each CTA supplies half of the N columns).
 void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh, int cg,
                   std::vector<__half>& hi, std::vector<__half>& lo, bool exact) {
-    const int NL = RD_G4 / cg, NB = CHUNK_N / cg;
+    const int NL = RD_G4 / cg, NB = MMA_N / cg;
     hi.assign((size_t)cg * (KG_H + KG_X) * NL * 8, __float2half(0.f));
     lo.assign(exact ? (size_t)cg * KG_H * NL * 8 : 0, __float2half(0.f));
     for (int rank = 0; rank < cg; ++rank)
         for (int nl = 0; nl < NL; ++nl) {
             const int cc = nl / NB, i = nl % NB;
-            const int n = cc * CHUNK_N + rank * NB + i;
+            const int n = cc * MMA_N + rank * NB + i;
             const int row = col_to_row(n);
+            // per-gate scale folded into the weights (see lstm_cell): gate = row / H in (i, f, g, o)
+            const bool is_g = row / RD_H == 2;
+            const double sc = exact ? (is_g ? (double)EXACT_SCALE_G : (double)EXACT_SCALE_IFO) : (is_g ? 1.0 : 0.5);
             for (int k = 0; k < RD_H; ++k) {
-                const float w = w_hh[row * RD_H + k];
+                const float w = (float)(sc * (double)w_hh[row * RD_H + k]);
                 const __half whi = __float2half_rn(w);
                 const size_t at = (((size_t)rank * (KG_H + KG_X) + k / 8) * NL + nl) * 8 + k % 8;
                 hi[at] = whi;
@@ -477,9 +599,9 @@ void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const
                 }
             }
             // x chunk: k = 0..3 W_ih hi, 4..7 W_ih lo, 8 bias hi, 9 bias lo
-            const float bias = b_ih[row] + b_hh[row];
+            const float bias = (float)(sc * ((double)b_ih[row] + (double)b_hh[row]));
             for (int cdx = 0; cdx < 4; ++cdx) {
-                const float w = w_ih[row * 4 + cdx];
+                const float w = (float)(sc * (double)w_ih[row * 4 + cdx]);
                 const __half whi = __float2half_rn(w);
                 const size_t a0 = (((size_t)rank * (KG_H + KG_X) + KG_H) * NL + nl) * 8;
                 hi[a0 + cdx] = whi;
@@ -516,6 +638,12 @@ int rd_tc_create(rd_handle* h, const float* w_hh, const float* w_ih, const float
     RD_CUDA(h, cudaMemcpy(s->d_img_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
     return RD_OK;
 }
+
+#ifdef RD_TC_PROFILE
+extern "C" int rd_debug_prof(unsigned long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 void rd_tc_destroy(rd_handle* h) {
     if (!h->tc) return;
