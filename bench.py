@@ -14,7 +14,9 @@ reads are 12 such batches; K of them are timed.  Per-GPU work is fixed as N grow
   e2e    the same metric through SeqModel.classify_host (C ABI rd_classify_host): HOST pinned
          buffers in, HOST labels out, H2D and D2H inside the timed region.
   roofline      K2 (the LSTM kernel) timed live with CUDA events inside the timed region
-                (rd_set_timing), algorithmic FLOPs per SURVEY.md §8d / DESIGN.md.
+                (rd_set_timing), algorithmic FLOPs per SURVEY.md §8d / DESIGN.md.  The default
+                precision is tc_exact (3-pass fp16 split on tcgen05, fp32-grade logits); the
+                single-pass tc_fast mode is timed once as well and reported under "fast_mode".
   cpu_baseline  the oracle port of the ribodetector_cpu loop (oracle/cpu_pipeline.py) on the
                 host cores, rank 0, N=1 only, bounded sample.
   --impl reference   times that same CPU arm as the line's value.
@@ -33,6 +35,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 READ_LEN = 100
+MUFU_PER_READ = {"fp32": 10 * 128 * READ_LEN, "tc_exact": 7 * 128 * READ_LEN, "tc_fast": 5 * 128 * READ_LEN}
+XU_LANES_PER_CLK_PER_SM = 16          # measured, tools/tc_rate.cu
 BATCH_READS = 1 << 22
 FLOP_PER_READ = 131072 * READ_LEN + 1024          # n*2*128*512 + 2*256*2
 METRIC = "reads/sec classified (100 bp)"
@@ -146,6 +150,7 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+    from ribodetector_b200 import shard
     from ribodetector_b200.model import SeqModel
     from ribodetector_b200.utils import synth
     from ribodetector_b200.utils.weights import load_weights
@@ -198,8 +203,7 @@ def run_ours(args, rank, world, local_rank):
     e0.record()
     for i in range(args.steps):
         step_device(i)
-    if world > 1:                                   # the path's only exchange: label counts
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    shard.allreduce_counts(counts)                  # the path's only exchange: int64[3] label counts (no-op at N=1)
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -208,6 +212,28 @@ def run_ours(args, rank, world, local_rank):
     timing = model.get_timing(reset=True)
     model.set_timing(False)
     total_counts = counts.cpu().tolist()
+
+    # ---- the single-pass mode, device-resident, for information (same timing protocol) -----------------
+    fast = None
+    if args.precision != "tc_fast" and not args.no_fast:
+        for i in range(3):
+            model.classify(devb[i % nbuf][0], devb[i % nbuf][1], READ_LEN, precision="tc_fast")
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True)
+        f1 = torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            model.classify(devb[i % nbuf][0], devb[i % nbuf][1], READ_LEN, precision="tc_fast")
+        f1.record()
+        barrier()
+        fast_ms = f0.elapsed_time(f1)
+        if world > 1:
+            tf = torch.tensor([fast_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            fast_ms = float(tf.item())
+        fast = {"precision": "tc_fast", "value": world * n * args.steps / (fast_ms / 1000.0), "unit": "reads/s",
+                "ms_per_step": fast_ms / args.steps,
+                "note": "single fp16 pass + tanh.approx: |dlogit| <= 5e-2, ~0.01-0.1 % label flips vs fp32"}
 
     # ---- end to end: host buffers through the public API ----------------------------------------------
     for i in range(min(args.warmup, 2)):
@@ -254,10 +280,18 @@ def run_ours(args, rank, world, local_rank):
                          "frac": achieved / peaks["tflops"], "traffic": None,
                          "peak_source": peaks["source"], "launch_ms": lstm_avg_s * 1000.0,
                          "flop_per_launch": FLOP_PER_READ * n,
-                         "share_of_step": lstm_ms / dev_ms if dev_ms else None},
+                         "share_of_step": lstm_ms / dev_ms if dev_ms else None,
+                         "co_bound": {"pipe": "xu (MUFU sigmoid/tanh)", "ops_per_read": MUFU_PER_READ[args.precision],
+                                      "achieved_gops": MUFU_PER_READ[args.precision] * n / lstm_avg_s / 1e9 if lstm_avg_s > 0 else 0.0,
+                                      "peak_gops": XU_LANES_PER_CLK_PER_SM * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) / 1e3,
+                                      "note": "peak = 16 MUFU lanes/clk/SM (measured) x 148 SMs x SM clock under load"}},
             "stage_ms": {k: v[0] / max(v[1], 1) for k, v in timing.items() if v[1]},
             "label_counts": total_counts, "e2e_label_counts_last_step": e2e_counts,
         }
+        cb = line["roofline"]["co_bound"]
+        cb["frac"] = cb["achieved_gops"] / cb["peak_gops"] if cb["peak_gops"] else None
+        if fast:
+            line["fast_mode"] = fast
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, sample = cpu_arm(weights, threads, args.cpu_batches, synth.SEED_BASE + 99)
@@ -276,15 +310,16 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RD_BENCH_PRECISION", "fp32"),
+    ap.add_argument("--precision", default=os.environ.get("RD_BENCH_PRECISION", "tc_exact"),
                     choices=["fp32", "tc_exact", "tc_fast"])
     ap.add_argument("--reads-per-step", type=int, default=BATCH_READS)
     ap.add_argument("--cpu-batches", type=int, default=12, help="1024-read batches per CPU worker in cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the informational tc_fast timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.steps is None:
-        args.steps = 4 if args.impl == "ours" else 3
+        args.steps = 12 if args.impl == "ours" else 3      # 12 x 2^22 reads = the 50 M reads of configs[1]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

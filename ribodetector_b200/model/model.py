@@ -38,7 +38,7 @@ class SeqModel:
     """BiLSTM(4→128) + Linear(256→2) classifier.  ``model(x)`` returns raw logits ``[B, 2]``."""
 
     def __init__(self, input_size=4, hidden_size=128, num_layers=1, num_classes=2,
-                 batch_first=True, bidirectional=True, pack_seq=True, precision="fp32"):
+                 batch_first=True, bidirectional=True, pack_seq=True, precision="tc_exact"):
         if (input_size, num_layers, num_classes, batch_first, bidirectional) != (4, 1, 2, True, True):
             raise ValueError("SeqModel kernels implement input_size=4, num_layers=1, num_classes=2, "
                              "batch_first=True, bidirectional=True (the shipped architecture)")

@@ -233,3 +233,74 @@ def test_kernel_launch_counter_moves(gpu_model):
     seq, off = synth.synth_reads_fixed(256, 50, 1)
     gpu_model.classify(seq, off, 50)
     assert gpu_model.kernel_launches() - before >= 6
+
+
+# ---- tensor-core modes at sizes the CPU oracle cannot reach: checked against the fp32 CUDA-core kernel ----
+def test_tc_modes_match_fp32_kernel_on_one_million_reads(gpu_model):
+    n = 1 << 20
+    seq, off = synth.synth_reads_fixed(n, 100, synth.SEED_BASE + 2)
+    ref = gpu_model.classify(seq, off, 100, precision="fp32")[0].cpu().numpy().astype(np.float64)
+    margin = np.abs(ref[:, 1] - ref[:, 0])
+    for prec in built_precisions(gpu_model):
+        if prec == "fp32":
+            continue
+        counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+        logits, _, labels = gpu_model.classify(seq, off, 100, precision=prec, counts=counts)
+        got = logits.cpu().numpy().astype(np.float64)
+        tol_l, _ = TOL[prec]
+        d = np.abs(got - ref).max()
+        flips = (got.argmax(1) != ref.argmax(1))
+        print("%s: max|dlogit| vs fp32 kernel = %.3e, label flips = %d / %d (in-band reads: %d)"
+              % (prec, d, flips.sum(), n, (margin <= 2 * tol_l).sum()))
+        assert d <= tol_l
+        assert not flips[margin > 2 * tol_l].any()
+        if prec == "tc_exact":
+            assert flips.sum() <= 10 and (margin <= 2 * tol_l).sum() < 1e-3 * n
+        else:
+            assert flips.mean() < 1e-3
+        lab = labels.cpu().numpy()
+        assert np.array_equal(lab, pairs.argmax_labels(got))
+        assert np.array_equal(counts.cpu().numpy(), pairs.counts(lab))
+
+
+def test_mixed_length_reads_config5_shape(gpu_model, numpy_oracle):
+    """BASELINE config 5 shape: 40-300 bp mixed, -l 300 (length-bucketed tiles of unequal step counts)."""
+    n = 200000
+    seq, off = synth.synth_reads(n, 40, 300, synth.SEED_BASE + 5)
+    ref = gpu_model.classify(seq, off, 300, precision="fp32")[0].cpu().numpy()
+    for prec in built_precisions(gpu_model):
+        got = gpu_model.classify(seq, off, 300, precision=prec)[0].cpu().numpy()
+        check_logits(got, ref, prec)
+    sub = np.arange(0, n, 97)[:1500]
+    reads = synth.to_strings(seq, off)
+    want = numpy_oracle.logits([reads[i] for i in sub], 300, "packed")
+    got = gpu_model.classify(seq, off, 300)[0].cpu().numpy()
+    check_logits(got[sub], want, "tc_exact")
+
+
+def test_paired_150bp_config4_shape_host_api(gpu_model):
+    """BASELINE config 3/4 shape: paired end, -e rrna, 150 bp; host pipeline == device kernels."""
+    n = 100000
+    s1, o1 = synth.synth_reads_fixed(n, 150, synth.SEED_BASE + 41)
+    s2, o2 = synth.synth_reads_fixed(n, 150, synth.SEED_BASE + 42)
+    r = gpu_model.classify_pairs_host(s1, o1, s2, o2, 150, mode="rrna", want_logits=True)
+    l1 = gpu_model.classify(s1, o1, 150)[0]
+    l2 = gpu_model.classify(s2, o2, 150)[0]
+    assert np.array_equal(r["logits1"].numpy(), l1.cpu().numpy())
+    assert np.array_equal(r["logits2"].numpy(), l2.cpu().numpy())
+    want = pairs.pair_labels(l1.cpu().numpy(), l2.cpu().numpy(), "rrna")
+    assert np.array_equal(r["labels"].numpy(), want)
+    assert np.array_equal(r["counts"].numpy(), pairs.counts(want))
+    assert int(r["counts"].sum()) == n
+
+
+def test_odd_tile_counts_and_tiny_batches(gpu_model, numpy_oracle):
+    """1, 127, 129, 385 reads: pad slots, a lone tile for the CTA pair, odd tile counts."""
+    for n in (1, 127, 129, 385):
+        seq, off = synth.synth_reads(n, 10, 90, 1000 + n)
+        reads = synth.to_strings(seq, off)
+        ref = numpy_oracle.logits(reads, 80, "packed")
+        for prec in built_precisions(gpu_model):
+            r = gpu_model.classify_host(seq, off, 80, precision=prec)
+            check_logits(r["logits"].numpy(), ref, prec)
+            assert int(r["counts"].sum()) == n
