@@ -1,0 +1,21 @@
+import sys, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+from ribodetector_b200.model import SeqModel
+from ribodetector_b200.utils import synth
+from ribodetector_b200.utils.weights import load_weights
+from oracle.model_numpy import NumpyOracle
+from oracle.model_torch import TorchOracle
+w = load_weights()
+m = SeqModel(); m.load_state_dict(w); m.to("cuda:0")
+o64 = NumpyOracle(w, np.float64); ot = TorchOracle(w)
+for L in (100, 200, 300):
+    seq, off = synth.synth_reads_fixed(3000, L, 900 + L)
+    reads = synth.to_strings(seq, off)
+    ref = o64.logits(reads, L, "packed")
+    tor = ot.logits_packed(reads, L)
+    out = {p: m.classify(seq, off, L, precision=p)[0].cpu().numpy().astype(np.float64) for p in ("fp32", "tc_exact", "tc_fast")}
+    print("L=%d  torch-fp32 vs f64: %.2e | fp32 kernel: %.2e  tc_exact: %.2e  tc_fast: %.2e | tc_exact vs fp32 kernel %.2e  vs torch %.2e" % (
+        L, np.abs(tor - ref).max(), np.abs(out["fp32"] - ref).max(), np.abs(out["tc_exact"] - ref).max(), np.abs(out["tc_fast"] - ref).max(),
+        np.abs(out["tc_exact"] - out["fp32"]).max(), np.abs(out["tc_exact"] - tor).max()))
+    d = np.abs(out["tc_exact"] - ref).max(1)
+    print("   tc_exact err percentiles 50/99/99.9/max: %.1e %.1e %.1e %.1e" % tuple(np.percentile(d, [50, 99, 99.9, 100])))
