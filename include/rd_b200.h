@@ -42,6 +42,7 @@ typedef struct rd_handle rd_handle;
                                 /* pack_sequence raises on it too (detect.py:685) → RuntimeError*/
 #define RD_ERR_NOMEM        4
 #define RD_ERR_UNSUPPORTED  5   /* shape outside what the kernels were built for               */
+#define RD_ERR_PARSE        6   /* malformed FASTQ/FASTA text (ValueError)                      */
 
 /* which "last valid step" convention:
  *   PACKED  = `ribodetector`     : detect.py:681-685 + model/model.py:32-37,114-119
@@ -71,6 +72,10 @@ typedef struct rd_handle rd_handle;
                               seq_encoder.py:130-145 encode_variable_len_read                   */
 
 #define RD_MAX_LEN 4096    /* largest supported -l / max_len */
+
+/* sequence file formats of the host-side record scanner / writer */
+#define RD_FMT_FASTQ 0
+#define RD_FMT_FASTA 1
 
 int rd_abi_version(void);
 
@@ -141,6 +146,33 @@ int rd_reverse_lut(rd_handle* h, int kmax, float* out);
  * (0 = K1 plan/encode, 1 = K2 LSTM, 2 = K3 tail, 3 = pair combine); reset != 0 clears them. */
 int rd_set_timing(rd_handle* h, int enable);
 int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int reset);
+
+/* ---- host side of the path's edges (no GPU involved) ------------------------------------------------
+ * Replaces seq_parser (data_loader/fastx_parser.py:15-55) for one buffer of UNCOMPRESSED text: scans
+ * complete records of buf[0..len) and returns their number (>= 0) or -RD_ERR_* (message from
+ * rd_fastx_last_error).  Reference semantics: FASTQ lines rstrip()ped, not upper-cased, a truncated
+ * final record dropped, blank lines an error; FASTA lines strip()ped, joined, upper-cased.
+ *   final_chunk  != 0 when buf ends at end of file (otherwise an unfinished record is left for the
+ *                next call: *consumed = offset of the first byte not consumed)
+ *   hdr          int64[2*max_records]  [begin, end) of each header line in buf (incl. '@' / '>')
+ *   plus, qual   int64[2*max_records]  FASTQ only: the '+' line and the quality line
+ *   seq_out      the sequences, concatenated, exactly as the reference's record[1] (this is the
+ *                `seq` argument of rd_classify*); seq_off int64[max_records+1] their offsets
+ * Stops early when max_records or seq_cap is reached. */
+int64_t rd_scan_fastx(const uint8_t* buf, int64_t len, int format, int final_chunk, int64_t max_records,
+                      int64_t* hdr, int64_t* plus, int64_t* qual, uint8_t* seq_out, int64_t seq_cap,
+                      int64_t* seq_off, int64_t* consumed);
+
+/* Replaces '\n'.join(record) + separate_reads / separate_paired_reads routing + the writes
+ * (detect.py:680,601-614,295-298): appends "header\nseq\n[plus\nqual\n]" of every record to the
+ * stream of its label (0 -> out_non, 1 -> out_rrna, -1 -> out_unc), preserving input order.
+ * sizes3 receives the byte counts; output pointers may be NULL (then only sizes are computed —
+ * call once with NULLs to size the buffers, once more to fill them). */
+int rd_partition_records(const uint8_t* buf, int format, int64_t n, const int64_t* hdr, const int64_t* plus,
+                         const int64_t* qual, const uint8_t* seq, const int64_t* seq_off, const int8_t* labels,
+                         uint8_t* out_non, uint8_t* out_rrna, uint8_t* out_unc, int64_t* sizes3, int threads);
+
+const char* rd_fastx_last_error(void);
 
 #ifdef __cplusplus
 }

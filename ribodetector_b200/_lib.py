@@ -9,7 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librd_b200.so")
 
-RD_OK, RD_ERR_INVALID, RD_ERR_CUDA, RD_ERR_EMPTY_READ, RD_ERR_NOMEM, RD_ERR_UNSUPPORTED = range(6)
+RD_OK, RD_ERR_INVALID, RD_ERR_CUDA, RD_ERR_EMPTY_READ, RD_ERR_NOMEM, RD_ERR_UNSUPPORTED, RD_ERR_PARSE = range(7)
+FMT = {"fastq": 0, "fasta": 1}
 SEM = {"packed": 0, "padded": 1}
 PREC = {"fp32": 0, "tc_exact": 1, "tc_fast": 2}
 PAIR = {"none": 0, "rrna": 1, "norrna": 2, "both": 3}
@@ -35,6 +36,9 @@ SIGNATURES = {
     "rd_reverse_lut": (_i, [_vp, _i, _vp]),
     "rd_set_timing": (_i, [_vp, _i]),
     "rd_get_timing": (_i, [_vp, _vp, _vp, _i]),
+    "rd_scan_fastx": (_i64, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "rd_partition_records": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "rd_fastx_last_error": (_c.c_char_p, []),
 }
 
 _lib = None

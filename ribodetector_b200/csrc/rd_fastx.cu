@@ -1,0 +1,206 @@
+// rd_fastx.cu — host side of the path's edges: FASTQ/FASTA record scanning and
+// label-partitioned record writing.  Pure host C++ (no kernels; lives in librd_b200.so so that one
+// library carries the whole C ABI).
+//
+// Replaces  seq_parser                    ribodetector/data_loader/fastx_parser.py:15-55
+//           the record text '\n'.join(r)  ribodetector/detect.py:680,711-712
+//           separate_reads routing        ribodetector/detect.py:601-614 (labels come from K3)
+// The reference parses with Python str methods, one line at a time (~1e5 reads/s per process); this
+// is one memchr-driven pass over the byte buffer.  Semantics kept: FASTQ lines are rstrip()ped and
+// NOT upper-cased, FASTA lines are strip()ped, joined and upper-cased, a truncated final FASTQ record
+// is dropped, blank lines inside a FASTQ file are an error (the reference raises IndexError).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/rd_b200.h"
+
+namespace {
+
+thread_local std::string g_fx_err;
+
+inline bool py_space(unsigned char c) {        // what str.strip() removes for ASCII text
+    return c == ' ' || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f);
+}
+
+}  // namespace
+
+extern "C" const char* rd_fastx_last_error(void) { return g_fx_err.c_str(); }
+
+extern "C" int64_t rd_scan_fastx(const uint8_t* buf, int64_t len, int format, int final_chunk, int64_t max_records,
+                                 int64_t* hdr, int64_t* plus, int64_t* qual, uint8_t* seq_out, int64_t seq_cap,
+                                 int64_t* seq_off, int64_t* consumed) {
+    g_fx_err.clear();
+    if (!buf || len < 0 || max_records < 0 || !hdr || !seq_out || !seq_off || !consumed ||
+        (format != RD_FMT_FASTQ && format != RD_FMT_FASTA) || (format == RD_FMT_FASTQ && (!plus || !qual))) {
+        g_fx_err = "rd_scan_fastx: bad arguments";
+        return -RD_ERR_INVALID;
+    }
+    int64_t n = 0, pos = 0, sfill = 0;
+    seq_off[0] = 0;
+    *consumed = 0;
+    if (format == RD_FMT_FASTQ) {
+        while (n < max_records) {
+            int64_t b[4], e[4], p = pos;
+            int k = 0;
+            for (; k < 4; ++k) {
+                if (p >= len) break;
+                const uint8_t* nl = static_cast<const uint8_t*>(memchr(buf + p, '\n', (size_t)(len - p)));
+                int64_t le;
+                if (nl) le = nl - buf;
+                else if (final_chunk) le = len;                // last line without a newline
+                else break;
+                int64_t r = le;
+                while (r > p && py_space(buf[r - 1])) --r;      // line.rstrip()
+                b[k] = p; e[k] = r;
+                p = nl ? le + 1 : len;
+            }
+            if (k < 4) break;                                   // incomplete record: wait for more bytes (or drop at EOF)
+            for (int j = 0; j < 4; ++j)
+                if (e[j] == b[j]) {
+                    g_fx_err = "FASTQ: blank line in record " + std::to_string(n) + " (the reference parser raises IndexError here)";
+                    return -RD_ERR_PARSE;
+                }
+            if (buf[b[0]] != '@') {
+                g_fx_err = "FASTQ: record " + std::to_string(n) + " does not start with '@'";
+                return -RD_ERR_PARSE;
+            }
+            const int64_t sl = e[1] - b[1];
+            if (sfill + sl > seq_cap) break;                    // caller's sequence buffer is full
+            memcpy(seq_out + sfill, buf + b[1], (size_t)sl);
+            sfill += sl;
+            hdr[2 * n] = b[0]; hdr[2 * n + 1] = e[0];
+            plus[2 * n] = b[2]; plus[2 * n + 1] = e[2];
+            qual[2 * n] = b[3]; qual[2 * n + 1] = e[3];
+            seq_off[++n] = sfill;
+            pos = p;
+        }
+        *consumed = pos;
+        return n;
+    }
+    // FASTA: a record is complete when the next header line (or EOF) is seen.  Every call starts at a
+    // record boundary: an unfinished record is rolled back and rescanned with the next chunk.
+    bool have_header = false;        // a '>' line opened the current record
+    bool open = false;               // current record has a header or (file start only) header-less sequence
+    int64_t rec_start = 0, hb = 0, he = 0, srec = 0, p = 0;
+    auto rollback = [&]() { sfill = srec; *consumed = open ? rec_start : p; seq_off[n] = sfill; };
+    while (true) {
+        if (p >= len) {
+            if (!final_chunk) { rollback(); return n; }
+            if (sfill > srec && n < max_records) {                 // `if seq != ''` at EOF (fastx_parser.py:54-55)
+                hdr[2 * n] = hb; hdr[2 * n + 1] = he;
+                seq_off[++n] = sfill;
+                *consumed = len;
+            } else if (sfill > srec) {
+                rollback();                                         // no room: hand it out on the next call
+            } else {
+                sfill = srec; *consumed = len;                      // trailing header without sequence is dropped
+            }
+            seq_off[n] = sfill;
+            return n;
+        }
+        const uint8_t* nl = static_cast<const uint8_t*>(memchr(buf + p, '\n', (size_t)(len - p)));
+        if (!nl && !final_chunk) { rollback(); return n; }          // partial last line
+        const int64_t le = nl ? nl - buf : len;
+        int64_t l = p, r = le;
+        while (r > l && py_space(buf[r - 1])) --r;
+        while (l < r && py_space(buf[l])) ++l;                      // line.strip()
+        if (r > l) {
+            if (buf[l] == '>') {
+                if (have_header) {                                  // closes the previous record, even an empty one
+                    hdr[2 * n] = hb; hdr[2 * n + 1] = he;
+                    seq_off[++n] = sfill;
+                    srec = sfill;
+                    open = false;
+                    if (n == max_records) { *consumed = p; return n; }
+                }
+                // (sequence lines before the very first header stay attached to it, like the reference)
+                if (!open) rec_start = p;
+                open = true; have_header = true; hb = l; he = r;
+            } else {
+                if (!open) { open = true; rec_start = p; hb = he = l; }
+                if (sfill + (r - l) > seq_cap) {
+                    if (n == 0) { g_fx_err = "FASTA: a single record exceeds the sequence buffer"; return -RD_ERR_NOMEM; }
+                    rollback();
+                    return n;
+                }
+                for (int64_t i = l; i < r; ++i) {
+                    const uint8_t c = buf[i];
+                    seq_out[sfill++] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c;   // .upper()
+                }
+            }
+        }
+        p = nl ? le + 1 : len;
+    }
+}
+
+// One output stream: header \n seq \n [plus \n qual \n] for every record whose label == want.
+static int64_t emit_class(const uint8_t* buf, int format, int64_t lo, int64_t hi, const int64_t* hdr, const int64_t* plus,
+                          const int64_t* qual, const uint8_t* seq, const int64_t* seq_off, const int8_t* labels, int want,
+                          uint8_t* out) {
+    int64_t w = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        if (labels[i] != want) continue;
+        const int64_t hl = hdr[2 * i + 1] - hdr[2 * i], sl = seq_off[i + 1] - seq_off[i];
+        if (out) { memcpy(out + w, buf + hdr[2 * i], (size_t)hl); out[w + hl] = '\n'; }
+        w += hl + 1;
+        if (out) { memcpy(out + w, seq + seq_off[i], (size_t)sl); out[w + sl] = '\n'; }
+        w += sl + 1;
+        if (format == RD_FMT_FASTQ) {
+            const int64_t pl = plus[2 * i + 1] - plus[2 * i], ql = qual[2 * i + 1] - qual[2 * i];
+            if (out) { memcpy(out + w, buf + plus[2 * i], (size_t)pl); out[w + pl] = '\n'; }
+            w += pl + 1;
+            if (out) { memcpy(out + w, buf + qual[2 * i], (size_t)ql); out[w + ql] = '\n'; }
+            w += ql + 1;
+        }
+    }
+    return w;
+}
+
+extern "C" int rd_partition_records(const uint8_t* buf, int format, int64_t n, const int64_t* hdr, const int64_t* plus,
+                                    const int64_t* qual, const uint8_t* seq, const int64_t* seq_off, const int8_t* labels,
+                                    uint8_t* out_non, uint8_t* out_rrna, uint8_t* out_unc, int64_t* sizes3, int threads) {
+    g_fx_err.clear();
+    if (!buf || n < 0 || !hdr || !seq || !seq_off || !labels || !sizes3 ||
+        (format != RD_FMT_FASTQ && format != RD_FMT_FASTA) || (format == RD_FMT_FASTQ && (!plus || !qual))) {
+        g_fx_err = "rd_partition_records: bad arguments";
+        return RD_ERR_INVALID;
+    }
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (n < 4096) threads = 1;
+    uint8_t* outs[3] = {out_non, out_rrna, out_unc};
+    const int wants[3] = {0, 1, -1};
+    // pass 1: bytes per (thread range, class); pass 2: fill at the prefix offsets
+    std::vector<int64_t> part((size_t)threads * 3, 0);
+    auto span = [&](int t, int64_t& lo, int64_t& hi) { lo = n * t / threads; hi = n * (t + 1) / threads; };
+    auto run = [&](bool fill) {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) {
+            auto work = [&, t]() {
+                int64_t lo, hi;
+                span(t, lo, hi);
+                for (int c = 0; c < 3; ++c) {
+                    if (fill) {
+                        if (!outs[c]) continue;
+                        int64_t base = 0;
+                        for (int u = 0; u < t; ++u) base += part[(size_t)u * 3 + c];
+                        emit_class(buf, format, lo, hi, hdr, plus, qual, seq, seq_off, labels, wants[c], outs[c] + base);
+                    } else {
+                        part[(size_t)t * 3 + c] = emit_class(buf, format, lo, hi, hdr, plus, qual, seq, seq_off, labels, wants[c], nullptr);
+                    }
+                }
+            };
+            if (threads == 1) work(); else pool.emplace_back(work);
+        }
+        for (auto& th : pool) th.join();
+    };
+    run(false);
+    for (int c = 0; c < 3; ++c) {
+        sizes3[c] = 0;
+        for (int t = 0; t < threads; ++t) sizes3[c] += part[(size_t)t * 3 + c];
+    }
+    if (out_non || out_rrna || out_unc) run(true);
+    return RD_OK;
+}

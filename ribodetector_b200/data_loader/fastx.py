@@ -1,0 +1,169 @@
+"""FASTQ/FASTA ingest and label-partitioned output on byte buffers.
+
+Mirrors the reference's loaders — ``get_seq_format`` / ``load_reads`` / ``get_seq_chunks``
+(``ribodetector/data_loader/seq_encoder.py:21-39,56-92``) on top of ``seq_parser``
+(``fastx_parser.py:15-55``) — but never builds Python strings per record: the file is read in large
+blocks, ``rd_scan_fastx`` (C ABI, host code in librd_b200.so) indexes the records, and the sequence
+bytes go to the GPU path as one buffer + offsets.  ``partition_records`` replaces the
+``'\\n'.join(record)`` / ``separate_reads`` / ``fh.write`` sequence (``detect.py:680,601-614,295-298``).
+"""
+import ctypes
+import gzip
+from mimetypes import guess_type
+from pathlib import Path
+
+import numpy as np
+
+from .. import _lib
+
+FA_EXTS = (".fasta", ".fa", ".fna", ".fas")
+FQ_EXTS = (".fq", ".fastq")
+
+
+def get_seq_format(seq_file):
+    """'fq' | 'fa' (+ 'gz') from the file name, same rules and errors as seq_encoder.py:21-39."""
+    encoding = guess_type(seq_file)[1]
+    if encoding is None:
+        encoding = ""
+    elif encoding == "gzip":
+        encoding = "gz"
+    else:
+        raise ValueError('Unknown file encoding: "{}"'.format(encoding))
+    name = Path(seq_file).stem if encoding == "gz" else Path(seq_file).name
+    ext = Path(name).suffix
+    if ext not in FA_EXTS + FQ_EXTS:
+        raise ValueError("""Unknown extension {}. Only fastq and fasta sequence formats are supported.
+And the file must end with one of ".fasta", ".fa", ".fna", ".fas", ".fq", ".fastq"
+and followed by ".gz" or ".gzip" if they are gzipped.""".format(ext))
+    return ("fa" if ext in FA_EXTS else "fq") + encoding
+
+
+def open_for_write(read_file):
+    """Binary twin of detect.py:729-741: gzip level 5 for names ending in 'gz', plain otherwise."""
+    if read_file.endswith("gz"):
+        return gzip.open(read_file, mode="wb", compresslevel=5)
+    return open(read_file, "wb")
+
+
+def _p(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+class RecordChunk:
+    """A block of file text plus the record index rd_scan_fastx built over it.  ``seq``/``seq_off``
+    are what the classifier consumes; ``hdr``/``plus``/``qual`` are [begin,end) pairs into ``buf``."""
+
+    def __init__(self, fmt, buf, n, hdr, plus, qual, seq, seq_off, lo=0):
+        self.format, self.buf, self.n = fmt, buf, n
+        self.hdr, self.plus, self.qual, self.seq, self.seq_off = hdr, plus, qual, seq, seq_off
+        self.lo = lo
+
+    def view(self, lo, hi):
+        """Records [lo, hi) of this chunk, sharing its buffers."""
+        return RecordChunk(self.format, self.buf, hi - lo, self.hdr[2 * lo:2 * hi],
+                           None if self.plus is None else self.plus[2 * lo:2 * hi],
+                           None if self.qual is None else self.qual[2 * lo:2 * hi],
+                           self.seq, self.seq_off[lo:hi + 1], self.lo + lo)
+
+    def records(self):
+        """The reference's record tuples (header, seq[, plus, qual]) as str — for tests / small inputs."""
+        b = self.buf.tobytes()
+        s = self.seq.tobytes()
+        out = []
+        for i in range(self.n):
+            h = b[self.hdr[2 * i]:self.hdr[2 * i + 1]].decode("latin-1")
+            q = s[self.seq_off[i]:self.seq_off[i + 1]].decode("latin-1")
+            if self.format == "fastq":
+                out.append((h, q, b[self.plus[2 * i]:self.plus[2 * i + 1]].decode("latin-1"),
+                            b[self.qual[2 * i]:self.qual[2 * i + 1]].decode("latin-1")))
+            else:
+                out.append((h, q))
+        return out
+
+
+class FastxReader:
+    """Iterate RecordChunks of up to ``max_records`` records over a (optionally gzipped) FASTQ/FASTA
+    file, holding one block of at most ``block_bytes`` of text at a time (bounded memory: the
+    reference's ``get_seq_chunks``, seq_encoder.py:75-87)."""
+
+    def __init__(self, path, max_records=1 << 22, block_bytes=1 << 28):
+        fmt = get_seq_format(path)
+        self.format = "fasta" if fmt.startswith("fa") else "fastq"
+        self.fh = gzip.open(path, "rb") if fmt.endswith("gz") else open(path, "rb", buffering=0)
+        self.max_records = int(max_records)
+        self.block_bytes = int(block_bytes)
+        self.tail = np.zeros(0, np.uint8)
+        self.eof = False
+        self.lib = _lib.load_library()
+        self.records_read = 0
+
+    def close(self):
+        self.fh.close()
+
+    def _fill(self, buf, start):
+        pos = start
+        mv = memoryview(buf)
+        while pos < buf.size:
+            k = self.fh.readinto(mv[pos:])
+            if not k:
+                self.eof = True
+                break
+            pos += k
+        return pos
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        while True:
+            if self.eof and self.tail.size == 0:
+                raise StopIteration
+            size = max(self.block_bytes, 2 * self.tail.size)
+            buf = np.empty(size, np.uint8)
+            buf[:self.tail.size] = self.tail
+            fill = self._fill(buf, self.tail.size) if not self.eof else self.tail.size
+            cap = self.max_records
+            hdr = np.empty(2 * cap, np.int64)
+            plus = np.empty(2 * cap, np.int64) if self.format == "fastq" else None
+            qual = np.empty(2 * cap, np.int64) if self.format == "fastq" else None
+            seq = np.empty(fill + 1, np.uint8)
+            seq_off = np.empty(cap + 1, np.int64)
+            consumed = ctypes.c_int64(0)
+            n = self.lib.rd_scan_fastx(_p(buf), fill, _lib.FMT[self.format], int(self.eof), cap, _p(hdr), _p(plus),
+                                       _p(qual), _p(seq), fill, _p(seq_off), ctypes.byref(consumed))
+            if n < 0:
+                msg = self.lib.rd_fastx_last_error().decode("utf-8", "replace")
+                raise ValueError("%s (record %d of the file)" % (msg, self.records_read))
+            c = consumed.value
+            self.tail = buf[c:fill].copy()
+            if n == 0:
+                if self.eof:
+                    self.tail = np.zeros(0, np.uint8)      # truncated final record: dropped like the reference
+                    raise StopIteration
+                if c == 0:
+                    self.block_bytes *= 2                    # one record larger than the block: grow and retry
+                continue
+            self.records_read += n
+            return RecordChunk(self.format, buf, int(n), hdr[:2 * n], None if plus is None else plus[:2 * n],
+                               None if qual is None else qual[:2 * n], seq, seq_off[:n + 1])
+
+
+def partition_records(chunk, labels, want=(True, True, True), threads=4):
+    """labels int8[n] in {0, 1, -1} → [non-rRNA bytes, rRNA bytes, unclassified bytes] (uint8 arrays,
+    None where not wanted) plus the three byte counts; record text and order as the reference."""
+    lib = _lib.load_library()
+    labels = np.ascontiguousarray(labels, dtype=np.int8)
+    if labels.size != chunk.n:
+        raise ValueError("labels/records mismatch")
+    sizes = np.zeros(3, np.int64)
+    args = (_p(chunk.buf), _lib.FMT[chunk.format], chunk.n, _p(chunk.hdr), _p(chunk.plus), _p(chunk.qual),
+            _p(chunk.seq), _p(chunk.seq_off), _p(labels))
+    rc = lib.rd_partition_records(*args, None, None, None, _p(sizes), int(threads))
+    if rc:
+        raise ValueError(lib.rd_fastx_last_error().decode())
+    outs = [np.empty(int(sizes[c]), np.uint8) if want[c] and sizes[c] else None for c in range(3)]
+    if any(o is not None for o in outs):
+        rc = lib.rd_partition_records(*args, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(sizes), int(threads))
+        if rc:
+            raise ValueError(lib.rd_fastx_last_error().decode())
+    return outs, sizes

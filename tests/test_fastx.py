@@ -1,0 +1,126 @@
+"""CPU: the host-side record scanner / writer (rd_scan_fastx, rd_partition_records — no GPU
+involved) against golden vectors produced by the REFERENCE's own parser (oracle/gen_golden_fastx.py)."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from ribodetector_b200.data_loader import FastxReader, get_seq_format, open_for_write, partition_records
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(GOLDEN, "fastx.json")) as f:
+        return json.load(f)
+
+
+def _read_all(path, **kw):
+    out = []
+    for ch in FastxReader(path, **kw):
+        out += ch.records()
+    return out
+
+
+def test_scanner_matches_reference_parser(golden, tmp_path):
+    for name, case in golden["cases"].items():
+        ext = ".fq" if case["type"] == "fastq" else ".fa"
+        p = tmp_path / (name + ext)
+        p.write_bytes(case["text"].encode("latin-1"))
+        want = [tuple(r) for r in case["records"]]
+        # one block; blocks far smaller than a record (forces carry-over / growth); 1 record per chunk
+        for kw in ({}, {"block_bytes": 5}, {"max_records": 1, "block_bytes": 64}):
+            assert _read_all(str(p), **kw) == want, (name, kw)
+        gz = tmp_path / (name + ext + ".gz")
+        with gzip.open(gz, "wb") as f:
+            f.write(case["text"].encode("latin-1"))
+        assert _read_all(str(gz), block_bytes=16) == want, name
+
+
+def test_format_sniffing_matches_reference(golden):
+    for name, want in golden["formats"].items():
+        if want == "ValueError":
+            with pytest.raises(ValueError):
+                get_seq_format(name)
+        else:
+            assert get_seq_format(name) == want
+
+
+def test_malformed_fastq_is_an_error(tmp_path):
+    for text in ("@r1\nACGT\n+\nIIII\n\n@r2\nAC\n+\nII\n",      # blank line: the reference raises IndexError
+                 "r1\nACGT\n+\nIIII\n"):                          # no '@'
+        p = tmp_path / "bad.fq"
+        p.write_text(text)
+        with pytest.raises(ValueError):
+            _read_all(str(p))
+
+
+def test_partition_preserves_order_and_text(golden, tmp_path):
+    """Output = '\\n'.join(record) + '\\n' per record, routed by label, input order (detect.py:601-614,295-298)."""
+    rng = np.random.default_rng(1)
+    recs = [("@r%d x" % i, "".join(rng.choice(list("ACGTN"), size=int(rng.integers(1, 80)))), "+", None) for i in range(20000)]
+    recs = [(h, s, p, "I" * len(s)) for h, s, p, _ in recs]
+    path = tmp_path / "big.fq"
+    path.write_text("".join("\n".join(r) + "\n" for r in recs))
+    labels_all = rng.choice(np.array([0, 1, -1], np.int8), size=len(recs), p=[0.7, 0.25, 0.05])
+    got = [b"", b"", b""]
+    seen = 0
+    for ch in FastxReader(str(path), max_records=6000):
+        lab = labels_all[seen:seen + ch.n]
+        for threads in (1, 5):
+            outs, sizes = partition_records(ch, lab, (True, True, True), threads)
+            for c, o in enumerate(outs):
+                assert (0 if o is None else o.size) == sizes[c]
+        for c, o in enumerate(outs):
+            got[c] += b"" if o is None else o.tobytes()
+        only_non, sizes2 = partition_records(ch, lab, (True, False, False), 2)
+        assert only_non[1] is None and only_non[2] is None and np.array_equal(sizes, sizes2)
+        seen += ch.n
+    assert seen == len(recs)
+    for c, want_label in enumerate((0, 1, -1)):
+        want = "".join("\n".join(r) + "\n" for r, l in zip(recs, labels_all) if l == want_label)
+        assert got[c].decode() == want
+
+
+def test_fasta_partition_writes_uppercased_joined_sequence(tmp_path):
+    p = tmp_path / "x.fa"
+    p.write_text(">a\nacgt\nnn\n>b\nGG\n")
+    ch = next(iter(FastxReader(str(p))))
+    outs, sizes = partition_records(ch, np.array([1, 0], np.int8))
+    assert outs[0].tobytes() == b">b\nGG\n" and outs[1].tobytes() == b">a\nACGTNN\n" and outs[2] is None
+
+
+def test_open_for_write_gz(tmp_path):
+    with open_for_write(str(tmp_path / "o.fq.gz")) as f:
+        f.write(b"@r\nA\n+\nI\n")
+    assert gzip.open(tmp_path / "o.fq.gz").read() == b"@r\nA\n+\nI\n"
+
+
+def test_cli_argument_surface():
+    """Flags and defaults of detect.py:764-798 / detect_cpu.py:777-807."""
+    from ribodetector_b200 import detect
+    a = detect.build_parser(True).parse_args(["-l", "100", "-i", "a.fq", "b.fq", "-o", "c.fq", "d.fq"])
+    assert (a.len, a.input, a.output, a.rrna, a.ensure, a.threads, a.memory, a.chunk_size, a.log, a.deviceid, a.config) == \
+        (100, ["a.fq", "b.fq"], ["c.fq", "d.fq"], None, "none", 10, 32, None, None, None, None)
+    c = detect.build_parser(False).parse_args(["-l", "50", "-i", "a.fq", "-o", "c.fq", "-e", "both", "-t", "3"])
+    assert c.threads == 3 and c.ensure == "both" and not hasattr(c, "memory") and not hasattr(c, "deviceid")
+    assert detect.build_parser(False).parse_args(["-l", "5", "-i", "a", "-o", "b"]).threads == 20
+    with pytest.raises(SystemExit):
+        detect.build_parser(True).parse_args(["-i", "a.fq", "-o", "c.fq"])          # -l is required
+
+
+def test_config_json_surface():
+    from ribodetector_b200.parse_config import ConfigParser
+    from ribodetector_b200 import detect
+    from ribodetector_b200.model import model as module_arch
+    cfg = ConfigParser.from_json(os.path.join(detect.cd, "config.json"))
+    assert cfg["arch"]["type"] == "SeqModel" and cfg["n_gpu"] == 1
+    assert set(cfg["arch"]["args"]) == {"input_size", "hidden_size", "num_layers", "num_classes", "batch_first",
+                                        "bidirectional", "pack_seq"}
+    assert set(cfg["state_file"]) == {"mcc", "recall"}
+    for v in cfg["state_file"].values():
+        assert os.path.exists(os.path.join(detect.cd, v))
+    m = cfg.init_obj("arch", module_arch)                       # the plugin seam: getattr(module, arch.type)(**args)
+    assert type(m).__name__ == "SeqModel" and m.pack_seq is True

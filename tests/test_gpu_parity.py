@@ -309,3 +309,72 @@ def test_odd_tile_counts_and_tiny_batches(gpu_model, numpy_oracle):
             r = gpu_model.classify_host(seq, off, 80, precision=prec)
             check_logits(r["logits"].numpy(), ref, prec)
             assert int(r["counts"].sum()) == n
+
+
+# ---- the command lines end to end (L-cli): files in, files out ------------------------------------------
+def _expected_files(records, labels, fmt="fastq"):
+    txt = {0: "", 1: "", -1: ""}
+    for r, l in zip(records, labels):
+        txt[int(l)] += "\n".join(r) + "\n"
+    return txt
+
+
+def test_cli_single_end_matches_oracle_routing(gpu_model, numpy_oracle, tmp_path):
+    """BASELINE config 0 shape (10k x 100 bp single-end FASTQ) through `ribodetector` and `ribodetector_cpu`."""
+    from ribodetector_b200 import detect, detect_cpu
+    n = 10000
+    seq, off = synth.synth_reads(n, 60, 130, synth.SEED_BASE)
+    reads = synth.to_strings(seq, off)
+    recs = [("@r%d" % i, s, "+", "I" * len(s)) for i, s in enumerate(reads)]
+    inp = tmp_path / "c1.fq"
+    inp.write_text("".join("\n".join(r) + "\n" for r in recs))
+    for mod, sem, flags in ((detect, "packed", ["-m", "8", "--chunk_size", "1"]), (detect_cpu, "padded", [])):
+        out, rr = tmp_path / ("non_%s.fq" % sem), tmp_path / ("rrna_%s.fq" % sem)
+        pred = mod.main(["-l", "100", "-i", str(inp), "-o", str(out), "-r", str(rr), "-t", "4"] + flags)
+        ref = numpy_oracle.logits(reads, 100, sem)
+        want_lab = pairs.argmax_labels(ref)
+        margin = np.abs(ref[:, 1] - ref[:, 0])
+        assert margin.min() > 4e-4, "seeded set has an in-band read; pick another seed"
+        want = _expected_files(recs, want_lab)
+        assert out.read_text() == want[0] and rr.read_text() == want[1]
+        assert (pred.num_seqs, pred.num_nonrrna, pred.num_rrna) == (n, int((want_lab == 0).sum()), int((want_lab == 1).sum()))
+
+
+def test_cli_paired_end_modes_and_gz(gpu_model, numpy_oracle, tmp_path):
+    import gzip
+    from ribodetector_b200 import detect
+    n = 3000
+    s1, o1 = synth.synth_reads(n, 50, 120, 31)
+    s2, o2 = synth.synth_reads(n, 50, 120, 32)
+    r1s, r2s = synth.to_strings(s1, o1), synth.to_strings(s2, o2)
+    rec1 = [("@p%d/1" % i, s, "+", "F" * len(s)) for i, s in enumerate(r1s)]
+    rec2 = [("@p%d/2" % i, s, "+", "F" * len(s)) for i, s in enumerate(r2s)]
+    f1, f2 = tmp_path / "r1.fq.gz", tmp_path / "r2.fq"
+    with gzip.open(f1, "wt") as f:
+        f.write("".join("\n".join(r) + "\n" for r in rec1))
+    f2.write_text("".join("\n".join(r) + "\n" for r in rec2))
+    l1, l2 = numpy_oracle.logits(r1s, 100, "packed"), numpy_oracle.logits(r2s, 100, "packed")
+    for mode in pairs.MODES:
+        want_lab = pairs.pair_labels(l1.astype(np.float32), l2.astype(np.float32), mode)
+        o = [tmp_path / ("o1_%s.fq" % mode), tmp_path / ("o2_%s.fq.gz" % mode)]
+        r = [tmp_path / ("x1_%s.fq" % mode), tmp_path / ("x2_%s.fq" % mode)]
+        pred = detect.main(["-l", "100", "-i", str(f1), str(f2), "-o", str(o[0]), str(o[1]), "-r", str(r[0]), str(r[1]),
+                            "-e", mode, "-t", "2"])
+        w1, w2 = _expected_files(rec1, want_lab), _expected_files(rec2, want_lab)
+        assert o[0].read_text() == w1[0] and gzip.open(o[1], "rt").read() == w2[0]
+        assert r[0].read_text() == w1[1] and r[1].read_text() == w2[1]
+        if mode == "both":
+            assert gzip.open(str(o[0]) + ".unclassified.gz", "rt").read() == w1[-1]
+            assert gzip.open(str(o[1]) + ".unclassified.gz", "rt").read() == w2[-1]
+            assert pred.num_unknown == int((want_lab == -1).sum()) > 0
+        assert pred.num_seqs == n and pred.num_rrna == int((want_lab == 1).sum())
+
+
+def test_cli_rejects_bad_file_counts(tmp_path):
+    from ribodetector_b200 import detect
+    (tmp_path / "a.fq").write_text("@r\nACGT\n+\nIIII\n")
+    with pytest.raises(RuntimeError):
+        detect.main(["-l", "100", "-i", str(tmp_path / "a.fq"), "-o", str(tmp_path / "o1.fq"), str(tmp_path / "o2.fq")])
+    (tmp_path / "a.txt").write_text("@r\nACGT\n+\nIIII\n")
+    with pytest.raises(ValueError):                      # unknown extension, like seq_encoder.py:35-37
+        detect.main(["-l", "100", "-i", str(tmp_path / "a.txt"), "-o", str(tmp_path / "o.fq")])
