@@ -35,6 +35,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 READ_LEN = 100
+# tensor FLOPs EXECUTED per algorithmic FLOP: K = 128 + 16 input chunk, x3 passes for the fp16 split
+EXECUTED_PER_ALGORITHMIC = {"fp32": 1.0, "tc_exact": 25.0 / 8.0, "tc_fast": 9.0 / 8.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch, per read (ncu --set full capture of a
+# 2^20-read launch, profiles/r1_ncu_tc_exact_summary.txt: 114.58 MB + 6.62 MB)
+NCU_DRAM_BYTES_PER_READ = (114.583808e6 + 6.619392e6) / 1048576
 MUFU_PER_READ = {"fp32": 10 * 128 * READ_LEN, "tc_exact": 7 * 128 * READ_LEN, "tc_fast": 5 * 128 * READ_LEN}
 XU_LANES_PER_CLK_PER_SM = 16          # measured, tools/tc_rate.cu
 BATCH_READS = 1 << 22
@@ -265,8 +270,8 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tc_exact": "f16x2-split/f32-acc", "tc_fast": "f16/f32-acc"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "100 bp single-end, 50M synthetic reads, 1xB200 (BASELINE configs[1]): "
-                                   "timed as %d batches of %d reads per GPU" % (args.steps, n),
+            "config": {"workload": "100 bp single-end, 50M synthetic reads per B200 (BASELINE configs[1]): "
+                                   "timed as %d batches of %d reads on each of %d GPU(s)" % (args.steps, n, world),
                        "read_len": READ_LEN, "reads_per_step_per_gpu": n, "precision": args.precision,
                        "semantics": "packed", "l2": "inputs larger than L2 (%.0f MB bases per step, 2 batches rotated)"
                                                     % (n * READ_LEN / 1e6),
@@ -277,7 +282,12 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "K2 forward LSTM (%s)" % args.precision,
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "frac": achieved / peaks["tflops"],
+                         "traffic": NCU_DRAM_BYTES_PER_READ * n if args.precision == "tc_exact" and READ_LEN == 100 else None,
+                         "traffic_note": "bytes per launch, scaled from the ncu capture of a 2^20-read launch; algorithmic "
+                                         "bytes per launch = %d" % (n * (READ_LEN + 8 + 8)),
+                         "executed_tflops": achieved * EXECUTED_PER_ALGORITHMIC[args.precision],
+                         "executed_frac": achieved * EXECUTED_PER_ALGORITHMIC[args.precision] / peaks["tflops"],
                          "peak_source": peaks["source"], "launch_ms": lstm_avg_s * 1000.0,
                          "flop_per_launch": FLOP_PER_READ * n,
                          "share_of_step": lstm_ms / dev_ms if dev_ms else None,

@@ -20,9 +20,13 @@ def default_weights_path():
 
 
 def load_weights(path=None):
-    """→ dict key → contiguous float32 ndarray.  Accepts .npz or a reference .pth/.pt."""
+    """→ dict key → contiguous float32 ndarray.  Accepts .npz, a reference .pth/.pt, or the reference's
+    .onnx export (what ribodetector_cpu loads, detect_cpu.py:74-75)."""
     path = path or default_weights_path()
-    if path.endswith(".npz"):
+    if path.endswith(".onnx"):
+        from .onnx_weights import load_onnx_state_dict
+        sd = load_onnx_state_dict(path)
+    elif path.endswith(".npz"):
         with np.load(path) as z:
             sd = {k: z[k] for k in z.files}
     else:

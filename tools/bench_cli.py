@@ -1,0 +1,53 @@
+"""L-cli measurement: wall clock of the `ribodetector` command line on a synthetic
+FASTQ file, parse + classify + write included.  python tools/bench_cli.py [n_reads] [read_len]"""
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ribodetector_b200 import detect                     # noqa: E402
+from ribodetector_b200.utils import synth                # noqa: E402
+
+
+def write_fastq(path, n, L, seed):
+    seq, _ = synth.synth_reads_fixed(n, L, seed)
+    w = 2 + 9 + 1 + L + 1 + 2 + L + 1                     # "@r%09d\n" seq "\n+\n" qual "\n"
+    rec = np.empty((n, w), np.uint8)
+    rec[:, 0], rec[:, 1] = ord("@"), ord("r")
+    idx = np.arange(n)
+    for d in range(9):
+        rec[:, 2 + 8 - d] = ord("0") + (idx // 10 ** d) % 10
+    rec[:, 11] = ord("\n")
+    rec[:, 12:12 + L] = seq.reshape(n, L)
+    rec[:, 12 + L] = ord("\n")
+    rec[:, 13 + L], rec[:, 14 + L] = ord("+"), ord("\n")
+    rec[:, 15 + L:15 + 2 * L] = ord("I")
+    rec[:, 15 + 2 * L] = ord("\n")
+    rec.tofile(path)
+    return rec.size
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+    L = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    d = tempfile.mkdtemp(prefix="rdcli_")
+    inp = os.path.join(d, "in.fq")
+    size = write_fastq(inp, n, L, synth.SEED_BASE + 7)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        pred = detect.main(["-l", str(L), "-i", inp, "-o", os.path.join(d, "non.fq"), "-r", os.path.join(d, "rrna.fq"),
+                            "-t", str(min(16, os.cpu_count() or 1))])
+        dt = time.perf_counter() - t0
+        print("run %d: %d reads, %.2f GB FASTQ in %.2f s = %.2f M reads/s (non-rRNA %d, rRNA %d)"
+              % (rep, pred.num_seqs, size / 1e9, dt, n / dt / 1e6, pred.num_nonrrna, pred.num_rrna), flush=True)
+    for f in os.listdir(d):
+        os.remove(os.path.join(d, f))
+    os.rmdir(d)
+
+
+if __name__ == "__main__":
+    main()
