@@ -158,10 +158,11 @@ int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int reset);
  *   plus, qual   int64[2*max_records]  FASTQ only: the '+' line and the quality line
  *   seq_out      the sequences, concatenated, exactly as the reference's record[1] (this is the
  *                `seq` argument of rd_classify*); seq_off int64[max_records+1] their offsets
- * Stops early when max_records or seq_cap is reached. */
+ * Stops early when max_records or seq_cap is reached.  `threads` host threads index a FASTQ buffer
+ * in parallel (records are exactly four lines, so newline counts per segment locate them). */
 int64_t rd_scan_fastx(const uint8_t* buf, int64_t len, int format, int final_chunk, int64_t max_records,
                       int64_t* hdr, int64_t* plus, int64_t* qual, uint8_t* seq_out, int64_t seq_cap,
-                      int64_t* seq_off, int64_t* consumed);
+                      int64_t* seq_off, int64_t* consumed, int threads);
 
 /* Replaces '\n'.join(record) + separate_reads / separate_paired_reads routing + the writes
  * (detect.py:680,601-614,295-298): appends "header\nseq\n[plus\nqual\n]" of every record to the

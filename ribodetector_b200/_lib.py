@@ -36,7 +36,7 @@ SIGNATURES = {
     "rd_reverse_lut": (_i, [_vp, _i, _vp]),
     "rd_set_timing": (_i, [_vp, _i]),
     "rd_get_timing": (_i, [_vp, _vp, _vp, _i]),
-    "rd_scan_fastx": (_i64, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "rd_scan_fastx": (_i64, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i]),
     "rd_partition_records": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rd_fastx_last_error": (_c.c_char_p, []),
 }

@@ -28,57 +28,118 @@ inline bool py_space(unsigned char c) {        // what str.strip() removes for A
 
 extern "C" const char* rd_fastx_last_error(void) { return g_fx_err.c_str(); }
 
+// ---- FASTQ: strictly 4 lines per record (the reference's state machine), so once the newline positions
+// are known every record is independent: count newlines per segment in parallel, prefix-sum, index.
+static int64_t scan_fastq(const uint8_t* buf, int64_t len, int final_chunk, int64_t max_records, int64_t* hdr,
+                          int64_t* plus, int64_t* qual, uint8_t* seq_out, int64_t seq_cap, int64_t* seq_off,
+                          int64_t* consumed, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (len < (1 << 20)) threads = 1;
+    std::vector<int64_t> cnt((size_t)threads + 1, 0);
+    auto seg = [&](int t) { return len * t / threads; };
+    auto par = [&](auto&& fn) {
+        if (threads == 1) { fn(0); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(fn, t);
+        for (auto& th : pool) th.join();
+    };
+    par([&](int t) {
+        int64_t c = 0;
+        const uint8_t* p = buf + seg(t);
+        const uint8_t* e = buf + seg(t + 1);
+        while (p < e) {
+            const uint8_t* q = static_cast<const uint8_t*>(memchr(p, '\n', (size_t)(e - p)));
+            if (!q) break;
+            ++c; p = q + 1;
+        }
+        cnt[(size_t)t + 1] = c;
+    });
+    for (int t = 0; t < threads; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+    const int64_t n_nl = cnt[(size_t)threads];
+    int64_t n_lines = n_nl;
+    const bool open_tail = final_chunk && len > 0 && buf[len - 1] != '\n';
+    if (open_tail) ++n_lines;                                   // last line without a newline
+    int64_t n = n_lines / 4;                                    // a truncated final record is dropped / left for later
+    if (n > max_records) n = max_records;
+    seq_off[0] = 0;
+    if (n == 0) { *consumed = 0; return 0; }
+    // line_end[i] = position of the newline ending line i (len for an open last line); only 4n needed
+    std::vector<int64_t> line_end((size_t)(4 * n));
+    par([&](int t) {
+        int64_t i = cnt[(size_t)t];
+        const uint8_t* p = buf + seg(t);
+        const uint8_t* e = buf + seg(t + 1);
+        while (p < e && i < 4 * n) {
+            const uint8_t* q = static_cast<const uint8_t*>(memchr(p, '\n', (size_t)(e - p)));
+            if (!q) break;
+            line_end[(size_t)i++] = q - buf;
+            p = q + 1;
+        }
+    });
+    if (4 * n > n_nl) line_end[(size_t)(4 * n - 1)] = len;     // the open last line closes the last record
+    std::vector<int64_t> bad((size_t)threads, -1);
+    std::vector<int> bad_kind((size_t)threads, 0);
+    par([&](int t) {
+        const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        for (int64_t r = lo; r < hi; ++r) {
+            int64_t b[4], e[4];
+            for (int k = 0; k < 4; ++k) {
+                const int64_t li = 4 * r + k;
+                b[k] = li == 0 ? 0 : line_end[(size_t)(li - 1)] + 1;
+                int64_t x = line_end[(size_t)li];
+                while (x > b[k] && py_space(buf[x - 1])) --x;   // line.rstrip()
+                e[k] = x;
+                if (x == b[k] && bad[(size_t)t] < 0) { bad[(size_t)t] = r; bad_kind[(size_t)t] = 1; }
+            }
+            if (e[0] > b[0] && buf[b[0]] != '@' && bad[(size_t)t] < 0) { bad[(size_t)t] = r; bad_kind[(size_t)t] = 2; }
+            hdr[2 * r] = b[0]; hdr[2 * r + 1] = e[0];
+            plus[2 * r] = b[2]; plus[2 * r + 1] = e[2];
+            qual[2 * r] = b[3]; qual[2 * r + 1] = e[3];
+            seq_off[r + 1] = e[1] - b[1];                       // length for now
+        }
+    });
+    for (int t = 0; t < threads; ++t)
+        if (bad[(size_t)t] >= 0) {
+            g_fx_err = bad_kind[(size_t)t] == 1
+                           ? "FASTQ: blank line in record " + std::to_string(bad[(size_t)t]) + " (the reference parser raises IndexError here)"
+                           : "FASTQ: record " + std::to_string(bad[(size_t)t]) + " does not start with '@'";
+            return -RD_ERR_PARSE;
+        }
+    int64_t fit = n;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t nxt = seq_off[r] + seq_off[r + 1];
+        if (nxt > seq_cap) { fit = r; break; }
+        seq_off[r + 1] = nxt;
+    }
+    n = fit;
+    par([&](int t) {
+        const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        for (int64_t r = lo; r < hi; ++r) {
+            const int64_t sb = (4 * r + 1 == 0 ? 0 : line_end[(size_t)(4 * r)] + 1);
+            memcpy(seq_out + seq_off[r], buf + sb, (size_t)(seq_off[r + 1] - seq_off[r]));
+        }
+    });
+    if (n == 0) { *consumed = 0; return 0; }
+    const int64_t last = line_end[(size_t)(4 * n - 1)];
+    *consumed = last >= len ? len : last + 1;
+    return n;
+}
+
 extern "C" int64_t rd_scan_fastx(const uint8_t* buf, int64_t len, int format, int final_chunk, int64_t max_records,
                                  int64_t* hdr, int64_t* plus, int64_t* qual, uint8_t* seq_out, int64_t seq_cap,
-                                 int64_t* seq_off, int64_t* consumed) {
+                                 int64_t* seq_off, int64_t* consumed, int threads) {
     g_fx_err.clear();
     if (!buf || len < 0 || max_records < 0 || !hdr || !seq_out || !seq_off || !consumed ||
         (format != RD_FMT_FASTQ && format != RD_FMT_FASTA) || (format == RD_FMT_FASTQ && (!plus || !qual))) {
         g_fx_err = "rd_scan_fastx: bad arguments";
         return -RD_ERR_INVALID;
     }
-    int64_t n = 0, pos = 0, sfill = 0;
+    int64_t n = 0, sfill = 0;
     seq_off[0] = 0;
     *consumed = 0;
-    if (format == RD_FMT_FASTQ) {
-        while (n < max_records) {
-            int64_t b[4], e[4], p = pos;
-            int k = 0;
-            for (; k < 4; ++k) {
-                if (p >= len) break;
-                const uint8_t* nl = static_cast<const uint8_t*>(memchr(buf + p, '\n', (size_t)(len - p)));
-                int64_t le;
-                if (nl) le = nl - buf;
-                else if (final_chunk) le = len;                // last line without a newline
-                else break;
-                int64_t r = le;
-                while (r > p && py_space(buf[r - 1])) --r;      // line.rstrip()
-                b[k] = p; e[k] = r;
-                p = nl ? le + 1 : len;
-            }
-            if (k < 4) break;                                   // incomplete record: wait for more bytes (or drop at EOF)
-            for (int j = 0; j < 4; ++j)
-                if (e[j] == b[j]) {
-                    g_fx_err = "FASTQ: blank line in record " + std::to_string(n) + " (the reference parser raises IndexError here)";
-                    return -RD_ERR_PARSE;
-                }
-            if (buf[b[0]] != '@') {
-                g_fx_err = "FASTQ: record " + std::to_string(n) + " does not start with '@'";
-                return -RD_ERR_PARSE;
-            }
-            const int64_t sl = e[1] - b[1];
-            if (sfill + sl > seq_cap) break;                    // caller's sequence buffer is full
-            memcpy(seq_out + sfill, buf + b[1], (size_t)sl);
-            sfill += sl;
-            hdr[2 * n] = b[0]; hdr[2 * n + 1] = e[0];
-            plus[2 * n] = b[2]; plus[2 * n + 1] = e[2];
-            qual[2 * n] = b[3]; qual[2 * n + 1] = e[3];
-            seq_off[++n] = sfill;
-            pos = p;
-        }
-        *consumed = pos;
-        return n;
-    }
+    if (format == RD_FMT_FASTQ)
+        return scan_fastq(buf, len, final_chunk, max_records, hdr, plus, qual, seq_out, seq_cap, seq_off, consumed, threads);
     // FASTA: a record is complete when the next header line (or EOF) is seen.  Every call starts at a
     // record boundary: an unfinished record is rolled back and rescanned with the next chunk.
     bool have_header = false;        // a '>' line opened the current record

@@ -9,6 +9,8 @@ bytes go to the GPU path as one buffer + offsets.  ``partition_records`` replace
 """
 import ctypes
 import gzip
+import queue
+import time
 from mimetypes import guess_type
 from pathlib import Path
 
@@ -53,17 +55,26 @@ class RecordChunk:
     """A block of file text plus the record index rd_scan_fastx built over it.  ``seq``/``seq_off``
     are what the classifier consumes; ``hdr``/``plus``/``qual`` are [begin,end) pairs into ``buf``."""
 
-    def __init__(self, fmt, buf, n, hdr, plus, qual, seq, seq_off, lo=0):
+    def __init__(self, fmt, buf, n, hdr, plus, qual, seq, seq_off, lo=0, parent=None, on_release=None):
         self.format, self.buf, self.n = fmt, buf, n
         self.hdr, self.plus, self.qual, self.seq, self.seq_off = hdr, plus, qual, seq, seq_off
         self.lo = lo
+        self._parent, self._on_release, self._released = parent, on_release, 0
 
     def view(self, lo, hi):
         """Records [lo, hi) of this chunk, sharing its buffers."""
         return RecordChunk(self.format, self.buf, hi - lo, self.hdr[2 * lo:2 * hi],
                            None if self.plus is None else self.plus[2 * lo:2 * hi],
                            None if self.qual is None else self.qual[2 * lo:2 * hi],
-                           self.seq, self.seq_off[lo:hi + 1], self.lo + lo)
+                           self.seq, self.seq_off[lo:hi + 1], self.lo + lo, parent=self._parent or self)
+
+    def release(self):
+        """Hand the chunk's buffers back to its reader once every record (all views) is done with."""
+        root = self._parent or self
+        root._released += self.n
+        if root._released >= root.n and root._on_release is not None:
+            cb, root._on_release = root._on_release, None
+            cb()
 
     def records(self):
         """The reference's record tuples (header, seq[, plus, qual]) as str — for tests / small inputs."""
@@ -86,21 +97,67 @@ class FastxReader:
     file, holding one block of at most ``block_bytes`` of text at a time (bounded memory: the
     reference's ``get_seq_chunks``, seq_encoder.py:75-87)."""
 
-    def __init__(self, path, max_records=1 << 22, block_bytes=1 << 28):
+    def __init__(self, path, max_records=1 << 22, block_bytes=1 << 28, threads=4):
         fmt = get_seq_format(path)
         self.format = "fasta" if fmt.startswith("fa") else "fastq"
         self.fh = gzip.open(path, "rb") if fmt.endswith("gz") else open(path, "rb", buffering=0)
+        self.plain = not fmt.endswith("gz")
+        self.file_pos = 0
+        self.pool = None
         self.max_records = int(max_records)
         self.block_bytes = int(block_bytes)
+        self.threads = int(threads)
         self.tail = np.zeros(0, np.uint8)
         self.eof = False
         self.lib = _lib.load_library()
         self.records_read = 0
+        self.wait_seconds = 0.0
+        # buffer sets are recycled (RecordChunk.release): fresh 256 MB allocations per chunk cost more in
+        # page faults than the scan itself
+        self.free = queue.Queue()
+        for _ in range(4):
+            self.free.put({})
 
     def close(self):
         self.fh.close()
+        if self.pool is not None:
+            self.pool.shutdown()
+
+    def _fill_parallel(self, buf, start):
+        """Plain files: positional reads of the block's slices on a few threads (page-cache copies scale
+        with threads; a single read() tops out near 2.5 GB/s)."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        if self.pool is None:
+            self.pool = ThreadPoolExecutor(max(1, min(self.threads, 8)))
+        fd = self.fh.fileno()
+        want = buf.size - start
+        k = max(1, min(self.threads, 8)) if want >= (1 << 24) else 1
+        step = max(1, -(-want // k))
+        mv = memoryview(buf)
+
+        def rd(i):
+            lo, got = i * step, 0
+            hi = min(want, lo + step)
+            while lo + got < hi:
+                r = os.preadv(fd, [mv[start + lo + got:start + hi]], self.file_pos + lo + got)
+                if r == 0:
+                    break
+                got += r
+            return got, hi - lo
+
+        total = 0
+        for got, span in self.pool.map(rd, range(k)):
+            total += got
+            if got < span:
+                self.eof = True
+                break
+        self.file_pos += total
+        return start + total
 
     def _fill(self, buf, start):
+        if self.plain:                       # (never mixed with read(): the positional reads keep their own offset)
+            return self._fill_parallel(buf, start)
         pos = start
         mv = memoryview(buf)
         while pos < buf.size:
@@ -119,24 +176,30 @@ class FastxReader:
             if self.eof and self.tail.size == 0:
                 raise StopIteration
             size = max(self.block_bytes, 2 * self.tail.size)
-            buf = np.empty(size, np.uint8)
-            buf[:self.tail.size] = self.tail
-            fill = self._fill(buf, self.tail.size) if not self.eof else self.tail.size
             cap = self.max_records
-            hdr = np.empty(2 * cap, np.int64)
-            plus = np.empty(2 * cap, np.int64) if self.format == "fastq" else None
-            qual = np.empty(2 * cap, np.int64) if self.format == "fastq" else None
-            seq = np.empty(fill + 1, np.uint8)
-            seq_off = np.empty(cap + 1, np.int64)
+            t_wait = time.perf_counter()
+            bs = self.free.get()                              # blocks while all sets are in flight (back-pressure)
+            self.wait_seconds += time.perf_counter() - t_wait
+            if bs.get("size", 0) < size or bs.get("cap", 0) < cap:
+                bs.clear()
+                bs.update(size=size, cap=cap, buf=np.empty(size, np.uint8), seq=np.empty(size + 1, np.uint8),
+                          hdr=np.empty(2 * cap, np.int64), seq_off=np.empty(cap + 1, np.int64),
+                          plus=np.empty(2 * cap, np.int64) if self.format == "fastq" else None,
+                          qual=np.empty(2 * cap, np.int64) if self.format == "fastq" else None)
+            buf, seq, hdr, plus, qual, seq_off = bs["buf"], bs["seq"], bs["hdr"], bs["plus"], bs["qual"], bs["seq_off"]
+            buf[:self.tail.size] = self.tail
+            fill = self._fill(buf[:size], self.tail.size) if not self.eof else self.tail.size
             consumed = ctypes.c_int64(0)
             n = self.lib.rd_scan_fastx(_p(buf), fill, _lib.FMT[self.format], int(self.eof), cap, _p(hdr), _p(plus),
-                                       _p(qual), _p(seq), fill, _p(seq_off), ctypes.byref(consumed))
+                                       _p(qual), _p(seq), fill, _p(seq_off), ctypes.byref(consumed), self.threads)
             if n < 0:
+                self.free.put(bs)
                 msg = self.lib.rd_fastx_last_error().decode("utf-8", "replace")
                 raise ValueError("%s (record %d of the file)" % (msg, self.records_read))
             c = consumed.value
             self.tail = buf[c:fill].copy()
             if n == 0:
+                self.free.put(bs)
                 if self.eof:
                     self.tail = np.zeros(0, np.uint8)      # truncated final record: dropped like the reference
                     raise StopIteration
@@ -145,12 +208,14 @@ class FastxReader:
                 continue
             self.records_read += n
             return RecordChunk(self.format, buf, int(n), hdr[:2 * n], None if plus is None else plus[:2 * n],
-                               None if qual is None else qual[:2 * n], seq, seq_off[:n + 1])
+                               None if qual is None else qual[:2 * n], seq, seq_off[:n + 1],
+                               on_release=lambda bs=bs: self.free.put(bs))
 
 
-def partition_records(chunk, labels, want=(True, True, True), threads=4):
+def partition_records(chunk, labels, want=(True, True, True), threads=4, scratch=None):
     """labels int8[n] in {0, 1, -1} → [non-rRNA bytes, rRNA bytes, unclassified bytes] (uint8 arrays,
-    None where not wanted) plus the three byte counts; record text and order as the reference."""
+    None where not wanted) plus the three byte counts; record text and order as the reference.
+    `scratch` (a dict the caller keeps) lets the output buffers be reused between calls."""
     lib = _lib.load_library()
     labels = np.ascontiguousarray(labels, dtype=np.int8)
     if labels.size != chunk.n:
@@ -161,7 +226,16 @@ def partition_records(chunk, labels, want=(True, True, True), threads=4):
     rc = lib.rd_partition_records(*args, None, None, None, _p(sizes), int(threads))
     if rc:
         raise ValueError(lib.rd_fastx_last_error().decode())
-    outs = [np.empty(int(sizes[c]), np.uint8) if want[c] and sizes[c] else None for c in range(3)]
+    outs = []
+    for c in range(3):
+        if not (want[c] and sizes[c]):
+            outs.append(None)
+        elif scratch is None:
+            outs.append(np.empty(int(sizes[c]), np.uint8))
+        else:
+            if scratch.get(c) is None or scratch[c].size < sizes[c]:
+                scratch[c] = np.empty(int(sizes[c] * 1.25) + 4096, np.uint8)
+            outs.append(scratch[c][:int(sizes[c])])
     if any(o is not None for o in outs):
         rc = lib.rd_partition_records(*args, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(sizes), int(threads))
         if rc:

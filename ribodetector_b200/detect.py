@@ -9,12 +9,13 @@ streaming pipeline here:
     writer thread   : rd_partition_records → non-rRNA / rRNA / unclassified files, input order kept
 
 Memory is bounded by the chunk size (``--chunk_size`` keeps its meaning: chunk = batch_size x
-chunk_size reads, ``detect.py:370-371``; without it chunks of 4 Mi reads are used), so there is no
+chunk_size reads, ``detect.py:370-371``; without it chunks of 1 Mi reads are used), so there is no
 whole-file mode to run out of RAM.  ``-m`` only feeds the reference's batch-size formula that the
 log line reports; ``-t`` sizes the host-side partition threads.
 """
 import argparse
 import math
+import time
 import os
 import queue
 import threading
@@ -27,7 +28,7 @@ from . import __version__
 from .parse_config import ConfigParser
 
 cd = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_CHUNK_READS = 1 << 22
+DEFAULT_CHUNK_READS = 1 << 20
 
 
 class colors:
@@ -111,6 +112,7 @@ class Predictor:
             self.logger.info('Choose batch size: {}{}{}{} based on the given GPU RAM size {}GB and max read length {}'.format(
                 colors.BOLD, colors.OKCYAN, self.batch_size, colors.ENDC, memory, self.len))
         self.chunk_reads = DEFAULT_CHUNK_READS if self.chunk_size is None else max(1, self.batch_size * self.chunk_size)
+        self._label_buf = [None] * len(self.models)
         self.run()
 
     # ---- the streaming pipeline (detect.py:121-523) ---------------------------------------------------
@@ -127,7 +129,10 @@ class Predictor:
             if e <= b:
                 return
             m = self.models[r]
-            out = {"labels": None}
+            if self._label_buf[r] is None or self._label_buf[r].numel() < e - b:
+                import torch
+                self._label_buf[r] = torch.empty(max(e - b, self.chunk_reads), dtype=torch.int8, pin_memory=True)
+            out = {"labels": self._label_buf[r][:e - b]}
             if self.is_paired:
                 res = m.classify_pairs_host(chunks[0].seq, chunks[0].seq_off[b:e + 1], chunks[1].seq,
                                             chunks[1].seq_off[b:e + 1], self.len, mode=self.args.ensure,
@@ -168,7 +173,8 @@ class Predictor:
     def run(self):
         from .data_loader import FastxReader, open_for_write, partition_records
         ends = 2 if self.is_paired else 1
-        readers = [FastxReader(f, max_records=self.chunk_reads) for f in self.input]
+        threads = max(1, min(int(self.args.threads), os.cpu_count() or 1))
+        readers = [FastxReader(f, max_records=self.chunk_reads, threads=max(1, threads // ends)) for f in self.input]
         want_unc = self.is_paired and self.args.ensure == 'both'
         if self.rrna is not None:
             self.logger.info('Writing output rRNA sequences into file: {}{}{}'.format(
@@ -184,16 +190,21 @@ class Predictor:
             self.logger.info('Writing unclassified sequences into file: {}{}{}'.format(
                 colors.OKYELLOW, ", ".join(unc), colors.ENDC))
 
-        q_in = queue.Queue(maxsize=2)
-        q_out = queue.Queue(maxsize=2)
+        q_in = queue.Queue(maxsize=3)
+        q_out = queue.Queue(maxsize=3)
         errors = []
-        threads = max(1, min(int(self.args.threads), os.cpu_count() or 1))
+
+        busy = {"read": 0.0, "classify": 0.0, "write": 0.0}
+        scratch = [{}, {}]
 
         def produce():
             try:
                 stream = self._pair_chunks(iter(readers[0]), iter(readers[1])) if self.is_paired else ((c,) for c in readers[0])
+                t0 = time.perf_counter()
                 for chunks in stream:
+                    busy["read"] += time.perf_counter() - t0
                     q_in.put(chunks)
+                    t0 = time.perf_counter()
             except BaseException as e:          # noqa: BLE001 — surfaced on the main thread
                 errors.append(e)
             finally:
@@ -206,14 +217,18 @@ class Predictor:
                     if item is None:
                         return
                     chunks, labels = item
+                    t0 = time.perf_counter()
                     for e in range(ends):
-                        outs, _ = partition_records(chunks[e], labels, (True, fh_rrna is not None, want_unc), threads)
+                        outs, _ = partition_records(chunks[e], labels, (True, fh_rrna is not None, want_unc), threads,
+                                                    scratch=scratch[e])
                         if outs[0] is not None:
                             fh_non[e].write(memoryview(outs[0]))
                         if outs[1] is not None:
                             fh_rrna[e].write(memoryview(outs[1]))
                         if outs[2] is not None:
                             fh_unc[e].write(memoryview(outs[2]))
+                        chunks[e].release()
+                    busy["write"] += time.perf_counter() - t0
             except BaseException as e:          # noqa: BLE001
                 errors.append(e)
                 while q_out.get() is not None:
@@ -230,7 +245,9 @@ class Predictor:
                 chunks = q_in.get()
                 if chunks is None or errors:
                     break
+                t0 = time.perf_counter()
                 labels, counts = self._classify(chunks)
+                busy["classify"] += time.perf_counter() - t0
                 num_seqs += chunks[0].n
                 total += counts
                 q_out.put((chunks, labels))
@@ -244,6 +261,9 @@ class Predictor:
         if errors:
             raise errors[0]
 
+        busy["read"] -= sum(r.wait_seconds for r in readers)      # time blocked on buffer back-pressure is not work
+        self.stage_seconds = busy
+        self.logger.debug('stage busy seconds: %s', busy)
         self.num_seqs, self.num_nonrrna, self.num_rrna, self.num_unknown = num_seqs, int(total[0]), int(total[1]), int(total[2])
         self.logger.info('Processed {}{}{}{} sequences in total'.format(colors.BOLD, colors.OKCYAN, num_seqs, colors.ENDC))
         self.logger.info('Detected {}{}{}{} non-rRNA sequences'.format(colors.BOLD, colors.OKCYAN, self.num_nonrrna, colors.ENDC))
@@ -282,7 +302,7 @@ none: give label based on the mean probability of read pair.
         args.add_argument('-m', '--memory', default=32, type=int, help='Amount (GB) of GPU RAM. (default: 12)')
     args.add_argument('--chunk_size', default=None, type=int,
                       help='Use this parameter when having low memory. Parsing the file in chunks.\n'
-                           'chunk = batch_size x chunk_size reads; without it chunks of 4 Mi reads are streamed.')
+                           'chunk = batch_size x chunk_size reads; without it chunks of 1 Mi reads are streamed.')
     args.add_argument('--log', default=None, type=str, help='Log file name')
     args.add_argument('--precision', default='tc_exact', choices=['tc_exact', 'tc_fast', 'fp32'],
                       help='(extension) arithmetic of the recurrent contraction: tc_exact = tcgen05 3-pass fp16 split,\nfp32-grade logits (default); tc_fast = one fp16 pass; fp32 = CUDA cores')

@@ -39,11 +39,18 @@ def main():
     size = write_fastq(inp, n, L, synth.SEED_BASE + 7)
     for rep in range(2):
         t0 = time.perf_counter()
-        pred = detect.main(["-l", str(L), "-i", inp, "-o", os.path.join(d, "non.fq"), "-r", os.path.join(d, "rrna.fq"),
-                            "-t", str(min(16, os.cpu_count() or 1))])
+        argv = ["-l", str(L), "-i", inp, "-o", os.path.join(d, "non.fq"), "-r", os.path.join(d, "rrna.fq"),
+                "-t", str(min(16, os.cpu_count() or 1))]
+        args = detect.build_parser(True).parse_args(argv)
+        pred = detect.Predictor(detect.ConfigParser.from_json(os.path.join(detect.cd, "config.json")), args)
+        pred.load_model()
+        t_load = time.perf_counter() - t0
+        pred.detect()
         dt = time.perf_counter() - t0
+        print("       load_model %.2f s, detect %.2f s" % (t_load, dt - t_load))
         print("run %d: %d reads, %.2f GB FASTQ in %.2f s = %.2f M reads/s (non-rRNA %d, rRNA %d)"
               % (rep, pred.num_seqs, size / 1e9, dt, n / dt / 1e6, pred.num_nonrrna, pred.num_rrna), flush=True)
+        print("       stage busy seconds:", {k: round(v, 3) for k, v in pred.stage_seconds.items()}, flush=True)
     for f in os.listdir(d):
         os.remove(os.path.join(d, f))
     os.rmdir(d)
