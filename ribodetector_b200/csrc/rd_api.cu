@@ -6,7 +6,7 @@
 #include <cstring>
 #include "rd_common.cuh"
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;     // rd_create has no handle to carry its message
 
 static int fail(rd_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_create_err = msg;

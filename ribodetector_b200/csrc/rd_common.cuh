@@ -44,6 +44,7 @@ struct rd_handle {
     float* d_bout = nullptr;       // [2]
     float* d_revlut = nullptr;     // [RD_MAX_LEN][5][2] reverse-half logit contributions
     rd_tc_state* tc = nullptr;
+    bool simt_attr_set = false;
 
     // scratch
     int64_t cap_n = 0;             // reads

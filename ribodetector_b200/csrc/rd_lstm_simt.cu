@@ -168,11 +168,10 @@ int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int L, float* d_logits, c
     if (n_tiles == 0) return RD_OK;
     int n_work = (int)(n_tiles * 2);
     int grid = h->sm_count < n_work ? h->sm_count : n_work;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->simt_attr_set) {      // per handle: function attributes are per device
         RD_CUDA(h, cudaFuncSetAttribute(lstm_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         SIMT_SMEM_BYTES));
-        attr_set = true;
+        h->simt_attr_set = true;
     }
     lstm_simt_kernel<<<grid, SIMT_THREADS, SIMT_SMEM_BYTES, st>>>(
         h->d_codes, h->d_splan, h->d_perm, L, n_work, reinterpret_cast<const float4*>(h->d_whh_t),

@@ -38,11 +38,18 @@ __device__ unsigned long long g_tc_prof[16];
 #define PROF_ADD(x)
 #endif
 
+#ifndef RD_TC_G_FAST
+#define RD_TC_G_FAST 4
+#endif
+#ifndef RD_TC_G_EXACT
+#define RD_TC_G_EXACT 4
+#endif
+
 namespace {
 
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TC_THREADS = EPI_THREADS + 32;          // + the MMA / allocator warp
+// activation warps: 4 TMEM lane quarters x G unit-group lanes; warp (q, g) owns the 8-unit groups j = g (mod G)
+__host__ __device__ constexpr int epi_warps(int G) { return 4 * G; }
+__host__ __device__ constexpr int tc_threads(int G) { return 4 * G * 32 + 32; }     // + the MMA / allocator warp
 constexpr int KCHUNKS = 8;                            // K-chunks of h (16 hidden units each) per step
 constexpr int MMA_N = 128;                            // D columns per MMA chunk = 32 hidden units x 4 gates
 constexpr int MMA_CHUNKS = RD_G4 / MMA_N;             // 4 per step
@@ -67,8 +74,8 @@ struct Cfg {
     static constexpr int OFF_LO = HI_BYTES;
     static constexpr int OFF_X = HI_BYTES + LO_BYTES;             // 2 x X_BYTES one-hot/bias A operand
     static constexpr int OFF_WOUT = OFF_X + 2 * X_BYTES;          // float [2][128]
-    static constexpr int OFF_PART = OFF_WOUT + 2 * RD_H * 4;      // float2 [2][128]
-    static constexpr int OFF_BAR = OFF_PART + 2 * RD_TILE * 8;    // mbarriers
+    static constexpr int OFF_PART = OFF_WOUT + 2 * RD_H * 4;      // float2 [4][128]
+    static constexpr int OFF_BAR = OFF_PART + 4 * RD_TILE * 8;    // mbarriers
     static constexpr int N_BAR = 2 + KCHUNKS + 2 * NBUF;
     static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
@@ -224,6 +231,7 @@ __device__ __forceinline__ float rcp_mufu(float x) {
 // carry a per-gate scale (rd_tc_create) so that the values read from tensor memory are directly
 // the arguments the activation hardware wants:
 //   FAST : zi,zf,zo = z/2, zg = z          sigmoid(z) = 0.5 tanh(z/2) + 0.5     (MUFU.TANH, 5 per unit)
+//          (option RD_TC_FAST_FMA_FORGET: zf = -z log2e and the forget gate on the FMA pipe, see sigmoid_fma)
 //   EXACT: zi,zf,zo = -z log2e, zg = -2 z log2e, so A = 2^zi = e^-z etc. and
 //            c' = f c + i g = (c (1+A)(1+B) + (1-B)(1+F)) / ((1+F)(1+A)(1+B))       A = e^-zi, B = e^-2zg, F = e^-zf
 //            h  = o tanh(c') = (1-D) / ((1+O)(1+D))                                  O = e^-zo, D = e^-2c'
@@ -233,6 +241,27 @@ __device__ __forceinline__ float rcp_mufu(float x) {
 constexpr float EXACT_SCALE_IFO = -1.4426950408889634f;     // -log2(e)
 constexpr float EXACT_SCALE_G = -2.8853900817779268f;       // -2 log2(e)
 constexpr float EXACT_CLAMP = 40.395461f;                   // 28 log2(e)
+// Kept as an option (off): measured on the box, evaluating the forget gate on the FMA pipe does NOT pay —
+// cycles per tile-step 6400 -> 6360 while the extra 16 instructions per unit pull the kernel onto the power
+// cap (SM clock 1965 -> 1905 MHz, 58.1 -> 56.7 M reads/s).  The FMA
+// rate is not the limit (tools/tc_rate.cu: FFMA and FMNMX each sustain ~125 lanes/clk/SM); the step time is
+// set by the per-chunk dependency structure, see DESIGN.md.
+#ifndef RD_TC_FAST_FMA_FORGET
+#define RD_TC_FAST_FMA_FORGET 0
+#endif
+constexpr bool FAST_FMA_FORGET = RD_TC_FAST_FMA_FORGET != 0;
+__device__ __forceinline__ float sigmoid_fma(float x) {       // 1 / (1 + 2^x), no MUFU
+    x = fminf(fmaxf(x, -60.0f), 60.0f);
+    const float t = x + 12582912.0f;                             // 1.5 * 2^23: round(x) lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);                      // [-0.5, 0.5]
+    const float p = fmaf(f, fmaf(f, fmaf(f, 0.05500893f, 0.24221097f), 0.6932829f), 1.0f);   // 2^f, rel err 1.0e-4
+    const float e = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));            // * 2^round(x)
+    const float d = 1.0f + e;
+    float y = __int_as_float(0x7EF311C7 - __float_as_int(d));   // 1/d to 5 %
+    y = fmaf(y, fmaf(-d, y, 1.0f), y);                          // Newton: 2.5e-3
+    y = fmaf(y, fmaf(-d, y, 1.0f), y);                          // 6.5e-6
+    return y;
+}
 template <bool EXACT>
 __device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo, float c_old, float& c_new, float& h_new) {
     if constexpr (EXACT) {
@@ -248,7 +277,7 @@ __device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo
         h_new = (1.0f - D) * rcp_mufu((1.0f + O) * (1.0f + D));
     } else {
         const float ig = fmaf(tanh_mufu(zi), 0.5f, 0.5f);
-        const float fg = fmaf(tanh_mufu(zf), 0.5f, 0.5f);
+        const float fg = FAST_FMA_FORGET ? sigmoid_fma(zf) : fmaf(tanh_mufu(zf), 0.5f, 0.5f);
         const float gg = tanh_mufu(zg);
         const float og = fmaf(tanh_mufu(zo), 0.5f, 0.5f);
         c_new = fmaf(fg, c_old, ig * gg);
@@ -270,8 +299,8 @@ __device__ __forceinline__ void st_x_row(uint32_t saddr, uint32_t code) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
-template <bool EXACT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool EXACT, int G>
+__global__ void __launch_bounds__(tc_threads(G), 1)
 lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ splan,
                const int32_t* __restrict__ perm, int L, int n_tiles,
                const uint8_t* __restrict__ img_hi,     // [CG][HI_BYTES] weight images (rd_tc_create)
@@ -282,6 +311,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                float* __restrict__ logits) {
     using C = Cfg<EXACT>;
     constexpr int CG = C::CG;
+    constexpr int EPI_WARPS = epi_warps(G), EPI_THREADS = EPI_WARPS * 32, TC_THREADS = tc_threads(G);
+    constexpr int SUBS = 16 / G;                      // 8-unit groups per warp per step
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_hi = s_base, s_lo = s_base + C::OFF_LO, s_x = s_base + C::OFF_X;
@@ -301,7 +332,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_tile, EPI_WARPS * CG);
-        for (int i = 0; i < KCHUNKS; ++i) mbar_init(bar_h + 8 * i, EPI_WARPS * CG);
+        for (int i = 0; i < KCHUNKS; ++i) mbar_init(bar_h + 8 * i, 8 * CG);      // 2 groups x 4 quarters publish a K-chunk
         for (int i = 0; i < NBUF; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, EPI_WARPS * CG);
@@ -443,7 +474,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
         }
     } else {
         // =============================== activation warps ===============================
-        const int q = warp & 3, par = warp >> 2;
+        const int q = warp & 3, par = warp >> 2;                         // lane quarter, unit-group lane g
         const int row = q * 32 + lane;                                   // read slot inside the tile
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const uint32_t x_row = s_x + (uint32_t)(row * 16);               // this read's k-group-0 row in x buffer 0
@@ -461,9 +492,9 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             const uint32_t myplan = have_tile ? splan[slot] : 0u;
             const int nf = (int)PLAN_NFWD(myplan);
             const uint8_t* cptr = codes + (int64_t)tile * L * RD_TILE + row;
-            float c[8][8];
+            float c[SUBS][8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
+            for (int g = 0; g < SUBS; ++g)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) c[g][u] = 0.f;
             float p0 = 0.f, p1 = 0.f;
@@ -486,10 +517,13 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                 const uint32_t wr = (uint32_t)(t & 1);                                   // h_t, x_{t+1} go to buffer t&1
                 const uint32_t awr = tmem + wr * C::ACOLS + lane_off;
 #pragma unroll
-                for (int cc = 0; cc < KCHUNKS; ++cc) {
-                    const int mc = cc >> 1, buf = mc & 1;
+                for (int cc = 0; cc < SUBS; ++cc) {
+                    // this warp's cc-th group of the step: j = cc*G + g; MMA chunk mc = j/4, K-chunk kc = j/2
+                    const int mc = (cc * G) >> 2, buf = mc & 1;
+                    const int j = cc * G + par;
+                    const bool first_of_chunk = G == 4 || (cc & 1) == 0, last_of_chunk = G == 4 || (cc & 1) == 1;
                     { PROF_T0();
-                    if ((cc & 1) == 0) mbar_wait(bar_full + 8 * buf, (mc >> 1) & 1);
+                    if (first_of_chunk) mbar_wait(bar_full + 8 * buf, (mc >> 1) & 1);
                     PROF_ADD(pe_full);
 #ifdef RD_TC_PROFILE
                     if (mc == 0) pe_full0 += clock64() - _p0;
@@ -498,10 +532,10 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                     tc_fence_after();
                     uint32_t v[32];
                     { PROF_T0();
-                    tmem_ld32(tmem + (uint32_t)(C::DCOL0 + buf * MMA_N + (cc & 1) * 64 + par * 32) + lane_off, v);
+                    tmem_ld32(tmem + (uint32_t)(C::DCOL0 + buf * MMA_N + (j & 3) * 32) + lane_off, v);
                     tc_wait_ld();
                     PROF_ADD(pe_ld); }
-                    if (cc & 1) {                                        // this warp has drained its part of the D buffer
+                    if (last_of_chunk) {                                 // this warp has drained its part of the D buffer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_empty + 8 * buf, 0); else mbar_arrive(bar_empty + 8 * buf); }
@@ -516,7 +550,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                         if (active) c[cc][u] = cn;
                     }
                     if (last) {        // fused FC: this thread's 8 units of W_out[:, :H] . h_fwd   (model.py:36)
-                        const int u0 = (2 * cc + par) * 8;
+                        const int u0 = j * 8;
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             p0 = fmaf(wout_s[u0 + u], hv[u], p0);
@@ -524,7 +558,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                         }
                     }
                     if (more) {
-                        const uint32_t hcol = awr + (uint32_t)(4 * (2 * cc + par));
+                        const uint32_t hcol = awr + (uint32_t)(4 * j);
                         if constexpr (EXACT) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
@@ -548,7 +582,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
                         tc_wait_st();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_h + 8 * cc, 0); else mbar_arrive(bar_h + 8 * cc); }
+                        const uint32_t hb = bar_h + 8 * (uint32_t)(j >> 1);
+                        if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(hb, 0); else mbar_arrive(hb); }
                         PROF_ADD(pe_st); }
                     }
                 }
@@ -561,10 +596,12 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             if (par == 0 && have_tile) {
                 const int32_t rd = perm[slot];
                 if (rd >= 0) {
-                    const float2 a = part_s[row], b = part_s[RD_TILE + row];
+                    float2 a = part_s[row];
+#pragma unroll
+                    for (int g = 1; g < G; ++g) { const float2 b = part_s[g * RD_TILE + row]; a.x += b.x; a.y += b.y; }
                     const float* lut = revlut + ((int64_t)PLAN_KREV(myplan) * 5 + PLAN_CREV(myplan)) * 2;
-                    float l0 = a.x + b.x + lut[0] + bout[0];
-                    float l1 = a.y + b.y + lut[1] + bout[1];
+                    float l0 = a.x + lut[0] + bout[0];
+                    float l1 = a.y + lut[1] + bout[1];
                     if (PLAN_INVALID(myplan)) { l0 = __int_as_float(0x7fc00000); l1 = l0; }
                     *reinterpret_cast<float2*>(logits + (int64_t)rd * 2) = make_float2(l0, l1);
                 }
@@ -607,8 +644,10 @@ void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const
             const int n = cc * MMA_N + rank * NB + i;
             const int row = col_to_row(n);
             // per-gate scale folded into the weights (see lstm_cell): gate = row / H in (i, f, g, o)
-            const bool is_g = row / RD_H == 2;
-            const double sc = exact ? (is_g ? (double)EXACT_SCALE_G : (double)EXACT_SCALE_IFO) : (is_g ? 1.0 : 0.5);
+            const int gate = row / RD_H;
+            const bool is_g = gate == 2;
+            const double sc = exact ? (is_g ? (double)EXACT_SCALE_G : (double)EXACT_SCALE_IFO)
+                                    : (is_g ? 1.0 : (gate == 1 && FAST_FMA_FORGET) ? (double)EXACT_SCALE_IFO : 0.5);
             for (int k = 0; k < RD_H; ++k) {
                 const float w = (float)(sc * (double)w_hh[row * RD_H + k]);
                 const __half whi = __float2half_rn(w);
@@ -636,6 +675,8 @@ void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const
 }
 
 }  // namespace
+
+constexpr int G_FAST = RD_TC_G_FAST, G_EXACT = RD_TC_G_EXACT;
 
 struct rd_tc_state {
     uint8_t* d_img_fast = nullptr;      // [1][147456]
@@ -680,17 +721,17 @@ int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float
     if (precision == RD_PREC_TC_FAST) {
         using C = Cfg<false>;
         if (!s->attr_fast) {
-            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<false, G_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
             s->attr_fast = true;
         }
         int grid = (int)(n_tiles < h->sm_count ? n_tiles : h->sm_count);
-        lstm_tc_kernel<false><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(
+        lstm_tc_kernel<false, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
             h->d_codes, h->d_splan, h->d_perm, L, (int)n_tiles, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
             h->d_revlut, d_logits);
     } else {
         using C = Cfg<true>;
         if (!s->attr_exact) {
-            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<true, G_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
             s->attr_exact = true;
         }
         int pairs = (int)((n_tiles + 1) / 2);
@@ -698,7 +739,7 @@ int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float
         int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(TC_THREADS);
+        cfg.blockDim = dim3(tc_threads(G_EXACT));
         cfg.dynamicSmemBytes = C::SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -709,7 +750,7 @@ int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float
         int nt = (int)n_tiles;
         const uint8_t* ihi = s->d_img_hi; const uint8_t* ilo = s->d_img_lo;
         const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
-        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true>, codes, splan, perm, L, nt, ihi, ilo, wout, bout, lut,
+        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, codes, splan, perm, L, nt, ihi, ilo, wout, bout, lut,
                                       d_logits));
     }
     h->launches += 1;

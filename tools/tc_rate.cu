@@ -124,6 +124,28 @@ __global__ void __launch_bounds__(256, 1) mufu_kernel(int iters, float* sink, lo
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// ---- 2b. FMA / ALU pipe rates ------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) fma_kernel(int iters, float* sink, long long* cyc) {
+    float x[8], a = 1.0001f + threadIdx.x * 1e-7f, b = 0.5f;
+    for (int j = 0; j < 8; ++j) x[j] = 0.001f * (threadIdx.x + 1) + j;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (MODE == 0) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[j]) : "f"(a), "f"(b));
+            else if (MODE == 1) asm volatile("min.f32 %0, %0, %1;" : "+f"(x[j]) : "f"(a));
+            else { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[j]) : "f"(a), "f"(b)); asm volatile("min.f32 %0, %0, %1;" : "+f"(x[j]) : "f"(a)); }
+        }
+    }
+    long long t1 = clock64();
+    float s = 0;
+    for (int j = 0; j < 8; ++j) s += x[j];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 // ---- 3. tcgen05.ld rate -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) ldtm_kernel(int iters, int nwarps, uint32_t* sink, long long* cyc) {
     __shared__ uint32_t tmem_s;
@@ -211,6 +233,19 @@ int main() {
         CK(cudaMemcpy(h, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
         double ops = (double)it * 8 * 256 * ((mode == 1 || mode == 5 || mode == 6) ? 2 : 1);
         printf("%-20s : %.2f MUFU instr-lanes/cycle/SM (%s)\n", names[mode], ops / (double)h[0], mode == 2 || mode == 4 ? "x2 results" : "x1");
+    }
+    printf("== FMA-pipe / ALU-pipe throughput (8 independent chains per thread) ==\n");
+    for (int nw : {4, 8, 16}) {
+        const int it = 4000;
+        const char* nm[] = {"ffma", "fmnmx (alu)", "ffma+fmnmx"};
+        for (int mode = 0; mode < 3; ++mode) {
+            if (mode == 0) fma_kernel<0><<<148, nw * 32>>>(it, d_sink, d_cyc);
+            if (mode == 1) fma_kernel<1><<<148, nw * 32>>>(it, d_sink, d_cyc);
+            if (mode == 2) fma_kernel<2><<<148, nw * 32>>>(it, d_sink, d_cyc);
+            CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(h, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+            printf("%2d warps/SM %-12s: %.1f lanes/cycle/SM\n", nw, nm[mode], (double)it * 8 * nw * 32 * (mode == 2 ? 2 : 1) / (double)h[0]);
+        }
     }
     printf("== tcgen05.ld.32x32b.x32 (4 KB per warp instruction) ==\n");
     for (int nw : {1, 4, 8}) {
