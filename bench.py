@@ -38,8 +38,8 @@ READ_LEN = 100
 # tensor FLOPs EXECUTED per algorithmic FLOP: K = 128 + 16 input chunk, x3 passes for the fp16 split
 EXECUTED_PER_ALGORITHMIC = {"fp32": 1.0, "tc_exact": 25.0 / 8.0, "tc_fast": 9.0 / 8.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch, per read (ncu --set full capture of a
-# 2^20-read launch, profiles/r1_ncu_tc_exact_summary.txt: 114.58 MB + 6.62 MB)
-NCU_DRAM_BYTES_PER_READ = (114.583808e6 + 6.619392e6) / 1048576
+# 2^20-read launch, profiles/r1_ncu_tc_exact_summary.txt: 114.87 MB + 8.89 MB)
+NCU_DRAM_BYTES_PER_READ = (114.873856e6 + 8.888320e6) / 1048576
 MUFU_PER_READ = {"fp32": 10 * 128 * READ_LEN, "tc_exact": 7 * 128 * READ_LEN, "tc_fast": 5 * 128 * READ_LEN}
 XU_LANES_PER_CLK_PER_SM = 16          # measured, tools/tc_rate.cu
 BATCH_READS = 1 << 22
