@@ -178,20 +178,39 @@ codes_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
 
 // ---------------------------------------------------------------------------------------------
 // one-hot materialisation (parity artefact of the reference encoders)
+// Each thread writes 4 consecutive one-hot rows (64 B; 2 KB contiguous per warp) with streaming stores:
+// the output is written once and never re-read by this library.  One integer division per 4 rows.
 __global__ void __launch_bounds__(256)
 onehot_padded_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int64_t n,
                      int L, float4* __restrict__ out) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * (int64_t)L) return;
-    int64_t i = idx / L;
-    int t = (int)(idx - i * L);
+    const int64_t total = n * (int64_t)L;
+    const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= total) return;
+    int64_t i;
+    int t;
+    if (total < ((int64_t)1 << 32)) {
+        const uint32_t q = (uint32_t)e0 / (uint32_t)L;
+        i = q; t = (int)((uint32_t)e0 - q * (uint32_t)L);
+    } else {
+        i = e0 / L; t = (int)(e0 - i * L);
+    }
     int64_t b = off[i];
     int64_t len = off[i + 1] - b;
-    uint32_t c = 4u;
-    if ((int64_t)t < len) c = base_code(seq[b + t]);
-    float4 v = make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f,
-                           c == 3u ? 1.f : 0.f);
-    out[idx] = v;                                 // 16-B stores, 512 B per warp
+    float4 v[4];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (e0 + k < total) {
+            while (t >= L) { t -= L; ++i; b = off[i]; len = off[i + 1] - b; }
+            uint32_t c = 4u;
+            if ((int64_t)t < len) c = base_code(seq[b + t]);
+            v[k] = make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f, c == 3u ? 1.f : 0.f);
+            ++t; ++cnt;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < cnt) __stcs(out + e0 + k, v[k]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -269,8 +288,8 @@ onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict_
     int64_t ro = row_off[w];
     for (int t = lane; t < m; t += 32) {
         uint32_t c = base_code(seq[b + t]);
-        out[ro + t] = make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f,
-                                  c == 3u ? 1.f : 0.f);
+        __stcs(out + ro + t, make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f,
+                                         c == 3u ? 1.f : 0.f));
     }
 }
 
@@ -304,7 +323,7 @@ int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, i
     if (n == 0) return RD_OK;
     if (layout == RD_ONEHOT_PADDED) {
         int64_t total = n * (int64_t)L;
-        onehot_padded_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        onehot_padded_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(
             d_seq, d_off, n, L, reinterpret_cast<float4*>(d_out));
         h->launches += 1;
     } else {
