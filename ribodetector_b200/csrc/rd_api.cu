@@ -27,10 +27,10 @@ static void free_scratch(rd_handle* h) {
     h->cap_n = h->cap_slots = h->cap_codes = 0;
 }
 
-static int ensure_scratch(rd_handle* h, int64_t n, int max_len) {
+static int ensure_scratch(rd_handle* h, int64_t n, int max_len, bool need_codes = false) {
     int64_t tiles = (n + RD_TILE - 1) / RD_TILE;
-    int64_t slots = tiles * RD_TILE;
-    int64_t codes = slots * (int64_t)max_len;
+    int64_t slots = (tiles + 1) * RD_TILE;                 // + one pad tile: the exact kernel works on tile pairs
+    int64_t codes = need_codes ? slots * (int64_t)max_len : 0;   // only the fp32 CUDA-core kernel wants the code buffer
     if (n <= h->cap_n && slots <= h->cap_slots && codes <= h->cap_codes) return RD_OK;
     RD_CUDA(h, cudaDeviceSynchronize());
     int64_t nn = std::max(n, h->cap_n), ss = std::max(slots, h->cap_slots), cc = std::max(codes, h->cap_codes);
@@ -221,18 +221,19 @@ extern "C" int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int res
 static int classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                            int semantics, int precision, float* d_logits, float* d_probs,
                            int8_t* d_labels, int64_t* d_counts, cudaStream_t st) {
-    int rc = ensure_scratch(h, n, max_len);
+    const bool need_codes = precision == RD_PREC_FP32;
+    int rc = ensure_scratch(h, n, max_len, need_codes);
     if (rc) return rc;
     int64_t tiles = 0;
     {
         StageTimer tm(h, 0, st);
-        rc = rd_launch_plan(h, d_seq, d_off, n, max_len, semantics, &tiles, st);
+        rc = rd_launch_plan(h, d_seq, d_off, n, max_len, semantics, need_codes, &tiles, st);
     }
     if (rc) return rc;
     {
         StageTimer tm(h, 1, st);
         if (precision == RD_PREC_FP32) rc = rd_launch_lstm_simt(h, tiles, max_len, d_logits, st);
-        else rc = rd_launch_lstm_tc(h, tiles, max_len, precision, d_logits, st);
+        else rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, precision, d_logits, st);
     }
     if (rc) return rc;
     if (d_probs || d_labels || d_counts) {
@@ -344,7 +345,7 @@ static int classify_host_impl(rd_handle* h, int ends,
         }
     rc = ensure_stage(h, chunk, max_bytes, ends, probs != nullptr);
     if (rc) return rc;
-    rc = ensure_scratch(h, chunk, max_len);
+    rc = ensure_scratch(h, chunk, max_len, precision == RD_PREC_FP32);
     if (rc) return rc;
     RD_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(int64_t) * 4, h->s_cmp));
 

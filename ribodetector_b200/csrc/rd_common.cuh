@@ -8,8 +8,10 @@
 //   perm    int32  [tiles*128]        slot → read index, slots sorted by nfwd DESCENDING
 //                                     (length-bucketed tiles, SURVEY §5 "long-context"); -1 = pad
 //   splan   uint32 [tiles*128]        plan[] gathered into slot order (0 for pad slots)
-//   codes   uint8  [tiles][L][128]    base codes 0..3 = A,C,G,T/U, 4 = zero row, transposed so
-//                                     that the 128 reads of a tile at step t are one 128-B line
+//   codes   uint8  [tiles][L][128]    ONLY for precision fp32 (CUDA-core kernel): base codes 0..3 = A,C,G,T/U,
+//                                     4 = zero row, transposed so the 128 reads of a tile at step t are one
+//                                     128-B line.  The tensor-core kernels read the caller's sequence bytes
+//                                     directly (one byte per read per step through L1) and convert in registers.
 //   logits  fp32   [n][2]             caller's output, input order
 #pragma once
 #include <cuda_runtime.h>
@@ -28,6 +30,17 @@
 #define PLAN_INVALID(p) (((p) >> 29) & 0x1u)
 
 struct rd_tc_state;                // tensor-core weight images (rd_lstm_tc.cu)
+
+// BASE_DICT of the reference (seq_encoder.py:11-18): A C G T U -> 0 1 2 3 3; everything else (N, IUPAC,
+// lower case, '-') -> 4 = the zero row
+__device__ __forceinline__ uint32_t rd_base_code(uint32_t b) {
+    uint32_t c = 4u;
+    c = (b == 'A') ? 0u : c;
+    c = (b == 'C') ? 1u : c;
+    c = (b == 'G') ? 2u : c;
+    c = (b == 'T' || b == 'U') ? 3u : c;
+    return c;
+}
 
 struct rd_handle {
     int device = 0;
@@ -93,12 +106,12 @@ struct rd_handle {
 
 // kernels' host launchers (each returns RD_OK / RD_ERR_*; all async on `st`)
 int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
-                   int semantics, int64_t* n_tiles_out, cudaStream_t st);
+                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st);
 int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                      int layout, float* d_out, int64_t* d_row_off, cudaStream_t st);
 int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int max_len, float* d_logits, cudaStream_t st);
-int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int max_len, int precision, float* d_logits,
-                      cudaStream_t st);
+int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
+                      int precision, float* d_logits, cudaStream_t st);
 int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_probs, int8_t* d_labels,
                    int64_t* d_counts, cudaStream_t st);
 int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n, int mode,

@@ -297,8 +297,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // ---------------------------------------------------------------------------------------------------
 template <bool EXACT, int G>
 __global__ void __launch_bounds__(tc_threads(G), 1)
-lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ splan,
-               const int32_t* __restrict__ perm, int L, int n_tiles,
+lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,   // the caller's reads
+               const uint32_t* __restrict__ splan, const int32_t* __restrict__ perm, int L, int n_tiles,
                const uint8_t* __restrict__ img_hi,     // [CG][HI_BYTES] weight images (rd_tc_create)
                const uint8_t* __restrict__ img_lo,     // [CG][LO_BYTES]
                const float* __restrict__ wout,         // [2][256]
@@ -487,7 +487,14 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             const bool have_tile = tile < n_tiles;
             const uint32_t myplan = have_tile ? splan[slot] : 0u;
             const int nf = (int)PLAN_NFWD(myplan);
-            const uint8_t* cptr = codes + (int64_t)tile * L * RD_TILE + row;
+            // this thread's read: its bytes are consumed one per step straight from the caller's buffer
+            // (consecutive steps hit the same 128-B line in L1; HBM sees every base once)
+            const int32_t my_rd = have_tile ? perm[slot] : -1;
+            const int64_t my_b = my_rd >= 0 ? off[my_rd] : 0;
+            const int64_t my_l64 = my_rd >= 0 ? off[my_rd + 1] - my_b : 0;
+            const int my_len = (int)(my_l64 < (int64_t)L ? my_l64 : (int64_t)L);
+            const uint8_t* cptr = seq + my_b;
+            auto code_at = [&](int t) -> uint32_t { return t < my_len ? rd_base_code(__ldg(cptr + t)) : 4u; };
             float c[SUBS][8];
 #pragma unroll
             for (int g = 0; g < SUBS; ++g)
@@ -496,8 +503,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             float p0 = 0.f, p1 = 0.f;
             uint32_t code_next = 4u, code_next2 = 4u;
             if (par == 0) {
-                const uint32_t code0 = (have_tile && T > 0) ? cptr[0] : 4u;
-                code_next = (have_tile && T > 1) ? cptr[RD_TILE] : 4u;
+                const uint32_t code0 = code_at(0);
+                code_next = code_at(1);
                 st_x_row(x_row + X_BYTES, code0);                        // x_0 -> operand buffer 1
                 fence_async_smem();
             }
@@ -506,7 +513,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_tile, 0); else mbar_arrive(bar_tile); }
 
             for (int t = 0; t < T; ++t) {
-                if (par == 0) code_next2 = (have_tile && t + 2 < T) ? cptr[(int64_t)(t + 2) * RD_TILE] : 4u;
+                if (par == 0) code_next2 = code_at(t + 2);
                 const bool active = t < nf;
                 const bool last = t == nf - 1;
                 const bool more = t + 1 < T;
@@ -590,7 +597,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ s
             part_s[par * RD_TILE + row] = make_float2(p0, p1);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             if (par == 0 && have_tile) {
-                const int32_t rd = perm[slot];
+                const int32_t rd = my_rd;
                 if (rd >= 0) {
                     float2 a = part_s[row];
 #pragma unroll
@@ -710,7 +717,8 @@ void rd_tc_destroy(rd_handle* h) {
     h->tc = nullptr;
 }
 
-int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float* d_logits, cudaStream_t st) {
+int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int L, int precision,
+                      float* d_logits, cudaStream_t st) {
     if (n_tiles == 0) return RD_OK;
     rd_tc_state* s = h->tc;
     if (!s) { h->err = "tensor-core state missing"; return RD_ERR_UNSUPPORTED; }
@@ -722,7 +730,7 @@ int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float
         }
         int grid = (int)(n_tiles < h->sm_count ? n_tiles : h->sm_count);
         lstm_tc_kernel<false, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
-            h->d_codes, h->d_splan, h->d_perm, L, (int)n_tiles, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
+            d_seq, d_off, h->d_splan, h->d_perm, L, (int)n_tiles, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
             h->d_revlut, d_logits);
     } else {
         using C = Cfg<true>;
@@ -742,11 +750,11 @@ int rd_launch_lstm_tc(rd_handle* h, int64_t n_tiles, int L, int precision, float
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const uint8_t* codes = h->d_codes; const uint32_t* splan = h->d_splan; const int32_t* perm = h->d_perm;
+        const uint32_t* splan = h->d_splan; const int32_t* perm = h->d_perm;
         int nt = (int)n_tiles;
         const uint8_t* ihi = s->d_img_hi; const uint8_t* ilo = s->d_img_lo;
         const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
-        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, codes, splan, perm, L, nt, ihi, ilo, wout, bout, lut,
+        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, d_seq, d_off, splan, perm, L, nt, ihi, ilo, wout, bout, lut,
                                       d_logits));
     }
     h->launches += 1;

@@ -10,15 +10,7 @@
 // All kernels here are HBM-bound byte/integer work: coalesced 128-B lines, no tensor cores.
 #include "rd_common.cuh"
 
-__device__ __forceinline__ uint32_t base_code(uint8_t b) {
-    // A C G T U → 0 1 2 3 3 ; everything else (N, IUPAC, lower case, '-') → 4 (zero row)
-    uint32_t c = 4u;
-    c = (b == 'A') ? 0u : c;
-    c = (b == 'C') ? 1u : c;
-    c = (b == 'G') ? 2u : c;
-    c = (b == 'T' || b == 'U') ? 3u : c;
-    return c;
-}
+__device__ __forceinline__ uint32_t base_code(uint8_t b) { return rd_base_code(b); }
 
 // ---------------------------------------------------------------------------------------------
 // plan: one thread per read
@@ -295,7 +287,7 @@ onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int L,
-                   int semantics, int64_t* n_tiles_out, cudaStream_t st) {
+                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st) {
     int64_t tiles = (n + RD_TILE - 1) / RD_TILE;
     *n_tiles_out = tiles;
     if (n == 0) return RD_OK;
@@ -312,8 +304,8 @@ int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int
     int kspan = L + 1;
     scatter_kernel<<<nb, 256, sizeof(int32_t) * 2 * kspan, st>>>(h->d_plan, n, h->d_hist, h->d_cursor,
                                                                  h->d_perm, h->d_splan, 0, kspan);
-    codes_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_seq, d_off, h->d_perm, h->d_splan, L, h->d_codes);
-    h->launches += 4;
+    if (need_codes) codes_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_seq, d_off, h->d_perm, h->d_splan, L, h->d_codes);
+    h->launches += need_codes ? 4 : 3;
     RD_CUDA(h, cudaGetLastError());
     return RD_OK;
 }

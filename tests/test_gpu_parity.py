@@ -237,7 +237,7 @@ def test_kernel_launch_counter_moves(gpu_model):
     before = gpu_model.kernel_launches()
     seq, off = synth.synth_reads_fixed(256, 50, 1)
     gpu_model.classify(seq, off, 50)
-    assert gpu_model.kernel_launches() - before >= 6
+    assert gpu_model.kernel_launches() - before >= 5          # plan, bucket scan, scatter, LSTM, tail
 
 
 # ---- tensor-core modes at sizes the CPU oracle cannot reach: checked against the fp32 CUDA-core kernel ----

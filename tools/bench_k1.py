@@ -59,7 +59,7 @@ def main():
         m.classify(s, o, L, precision="tc_fast")
     tm = m.get_timing(reset=True)
     t = tm["plan"][0] / tm["plan"][1] / 1e3
-    nbytes = n * L + 8 * n + n * L + 12 * n            # bases + offsets read; codes + plan/perm/splan written
+    nbytes = 8 * n + n + 12 * n                        # offsets + last base read; plan/perm/splan written (tc modes)
     out["kernels"]["k1_plan_codes"] = {"ms": t * 1e3, "algorithmic_bytes": nbytes, "gbs": nbytes / t / 1e9, "frac_of_peak": nbytes / t / 1e9 / peak}
     t = tm["tail"][0] / tm["tail"][1] / 1e3
     nbytes = 17 * n
