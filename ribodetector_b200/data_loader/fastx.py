@@ -51,6 +51,19 @@ def _p(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
+def _host_array(n, dtype, pinned):
+    """numpy array, page-locked when a CUDA device is there: the sequence bytes and offsets go to the
+    GPU by cudaMemcpyAsync straight from these recycled buffers."""
+    if pinned:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(n, dtype={np.uint8: torch.uint8, np.int64: torch.int64}[dtype], pin_memory=True).numpy()
+        except Exception:                    # noqa: BLE001 — fall back to pageable memory
+            pass
+    return np.empty(n, dtype)
+
+
 class RecordChunk:
     """A block of file text plus the record index rd_scan_fastx built over it.  ``seq``/``seq_off``
     are what the classifier consumes; ``hdr``/``plus``/``qual`` are [begin,end) pairs into ``buf``."""
@@ -97,7 +110,7 @@ class FastxReader:
     file, holding one block of at most ``block_bytes`` of text at a time (bounded memory: the
     reference's ``get_seq_chunks``, seq_encoder.py:75-87)."""
 
-    def __init__(self, path, max_records=1 << 22, block_bytes=1 << 28, threads=4):
+    def __init__(self, path, max_records=1 << 22, block_bytes=1 << 28, threads=4, pinned=False):
         fmt = get_seq_format(path)
         self.format = "fasta" if fmt.startswith("fa") else "fastq"
         self.fh = gzip.open(path, "rb") if fmt.endswith("gz") else open(path, "rb", buffering=0)
@@ -107,6 +120,7 @@ class FastxReader:
         self.max_records = int(max_records)
         self.block_bytes = int(block_bytes)
         self.threads = int(threads)
+        self.pinned = bool(pinned)
         self.tail = np.zeros(0, np.uint8)
         self.eof = False
         self.lib = _lib.load_library()
@@ -182,8 +196,8 @@ class FastxReader:
             self.wait_seconds += time.perf_counter() - t_wait
             if bs.get("size", 0) < size or bs.get("cap", 0) < cap:
                 bs.clear()
-                bs.update(size=size, cap=cap, buf=np.empty(size, np.uint8), seq=np.empty(size + 1, np.uint8),
-                          hdr=np.empty(2 * cap, np.int64), seq_off=np.empty(cap + 1, np.int64),
+                bs.update(size=size, cap=cap, buf=np.empty(size, np.uint8), seq=_host_array(size + 1, np.uint8, self.pinned),
+                          hdr=np.empty(2 * cap, np.int64), seq_off=_host_array(cap + 1, np.int64, self.pinned),
                           plus=np.empty(2 * cap, np.int64) if self.format == "fastq" else None,
                           qual=np.empty(2 * cap, np.int64) if self.format == "fastq" else None)
             buf, seq, hdr, plus, qual, seq_off = bs["buf"], bs["seq"], bs["hdr"], bs["plus"], bs["qual"], bs["seq_off"]

@@ -174,7 +174,8 @@ class Predictor:
         from .data_loader import FastxReader, open_for_write, partition_records
         ends = 2 if self.is_paired else 1
         threads = max(1, min(int(self.args.threads), os.cpu_count() or 1))
-        readers = [FastxReader(f, max_records=self.chunk_reads, threads=max(1, threads // ends)) for f in self.input]
+        readers = [FastxReader(f, max_records=self.chunk_reads, threads=max(1, threads // ends), pinned=True)
+                   for f in self.input]
         want_unc = self.is_paired and self.args.ensure == 'both'
         if self.rrna is not None:
             self.logger.info('Writing output rRNA sequences into file: {}{}{}'.format(
