@@ -129,8 +129,6 @@ class FastxReader:
         # buffer sets are recycled (RecordChunk.release): fresh 256 MB allocations per chunk cost more in
         # page faults than the scan itself
         self.free = queue.Queue()
-        for _ in range(4):
-            self.free.put({})
 
     def close(self):
         self.fh.close()
@@ -191,9 +189,10 @@ class FastxReader:
                 raise StopIteration
             size = max(self.block_bytes, 2 * self.tail.size)
             cap = self.max_records
-            t_wait = time.perf_counter()
-            bs = self.free.get()                              # blocks while all sets are in flight (back-pressure)
-            self.wait_seconds += time.perf_counter() - t_wait
+            try:
+                bs = self.free.get_nowait()                   # a recycled set (RecordChunk.release), else a fresh one:
+            except queue.Empty:                               # callers that never release just allocate per chunk
+                bs = {}
             if bs.get("size", 0) < size or bs.get("cap", 0) < cap:
                 bs.clear()
                 bs.update(size=size, cap=cap, buf=np.empty(size, np.uint8), seq=_host_array(size + 1, np.uint8, self.pinned),

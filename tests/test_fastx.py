@@ -124,3 +124,70 @@ def test_config_json_surface():
         assert os.path.exists(os.path.join(detect.cd, v))
     m = cfg.init_obj("arch", module_arch)                       # the plugin seam: getattr(module, arch.type)(**args)
     assert type(m).__name__ == "SeqModel" and m.pack_seq is True
+
+
+REF_ROOT = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ROOT), reason="reference checkout not mounted (GPU box)")
+def test_scanner_differential_fuzz_against_reference_parser(tmp_path):
+    """Random FASTQ/FASTA texts (odd whitespace, CRLF, truncated tails, multi-line FASTA, '@' qualities)
+    through rd_scan_fastx at several block sizes vs the reference's seq_parser imported unmodified."""
+    import io
+    import sys
+    import types
+    sys.path.insert(0, REF_ROOT)
+    bio, seqm = types.ModuleType("Bio"), types.ModuleType("Bio.Seq")
+    seqm.Seq = object
+    sys.modules.setdefault("Bio", bio)
+    sys.modules.setdefault("Bio.Seq", seqm)
+    from ribodetector.data_loader.fastx_parser import seq_parser
+    rng = np.random.default_rng(7)
+    alpha = list("ACGTNacgtnRYU-")
+
+    def rseq(lo, hi):
+        return "".join(rng.choice(alpha, size=int(rng.integers(lo, hi))))
+
+    for trial in range(60):
+        eol = "\r\n" if trial % 3 == 0 else "\n"
+        pad = lambda: " " * int(rng.integers(0, 3)) if trial % 4 == 0 else ""     # noqa: E731
+        n = int(rng.integers(0, 40))
+        if trial % 2 == 0:
+            typ, ext, text = "fastq", ".fq", ""
+            for i in range(n):
+                s = rseq(1, 120)
+                q = "".join(rng.choice(list("@+I#5"), size=len(s)))
+                text += "".join(["@r%d d" % i, pad(), eol, s, pad(), eol, "+", "x" * int(rng.integers(0, 2)), pad(), eol,
+                                 q, pad(), eol])
+            if n and rng.random() < 0.4:                       # truncated tail / missing final newline
+                text = text[:len(text) - int(rng.integers(1, 30))]
+        else:
+            typ, ext, text = "fasta", ".fa", ""
+            for i in range(n):
+                text += ">s%d%s%s" % (i, pad(), eol)
+                for _ in range(int(rng.integers(0, 4))):
+                    text += pad() + rseq(1, 70) + pad() + eol
+                if rng.random() < 0.2:
+                    text += eol
+            if n and rng.random() < 0.3:
+                text = text.rstrip("\r\n")
+        try:
+            want = [tuple(r) for r in seq_parser(io.StringIO(text, newline=None), typ)]
+            ref_error = False
+        except IndexError:                                     # blank line inside a FASTQ record
+            ref_error = True
+        p = tmp_path / ("t%d%s" % (trial, ext))
+        p.write_bytes(text.encode("latin-1"))
+        for kw in ({}, {"block_bytes": 7}, {"max_records": 3, "block_bytes": 50}):
+            if ref_error:
+                with pytest.raises(ValueError):
+                    _read_all(str(p), **kw)
+            else:
+                try:
+                    got = _read_all(str(p), **kw)
+                except ValueError:
+                    # the only tolerated divergence: a non-'@' line where a header is expected, which the
+                    # reference silently turns into a garbage record (fastx_parser.py:31-36)
+                    assert typ == "fastq" and any(not l.startswith("@") for l in text.splitlines()[0::4] if l.strip())
+                    continue
+                assert got == want, (trial, kw)
