@@ -9,20 +9,21 @@
 //           activation warps with tcgen05.st (fp16; EXACT: fp16 hi + fp16 lo residual),
 //       B = the recurrent weights, staged ONCE per CTA into shared memory by the TMA bulk-copy
 //           engine (cp.async.bulk) in the K-major SWIZZLE_NONE canonical layout,
-//       D = fp32 accumulators in tensor memory, produced in 8 column chunks of 64 (= 16 hidden
+//       D = fp32 accumulators in tensor memory, produced in 4 column chunks of 128 (= 32 hidden
 //           units x 4 gates, gate-interleaved so one tcgen05.ld.32x32b.x32 hands a thread i,f,g,o of
-//           8 units of its read) through a ring of NBUF chunk buffers.
-// Eight activation warps (4 lane quarters x 2 unit-group parities) drain the chunks: sigmoid/tanh,
-// cell update in fp32 registers, h_t back into the other A buffer.  One elected thread issues the
-// MMAs.  The recurrence is pipelined as a wavefront: chunk 0 of step t+1 accumulates K-chunk kc as
+//           8 units of its read) through a ring of 2 chunk buffers (N = 128 is the smallest N at which a
+//           tcgen05.mma costs its ~78-cycle floor, tools/tc_rate.cu).
+// Sixteen activation warps (4 TMEM lane quarters x 4 unit-group lanes) drain the chunks: sigmoid/tanh,
+// cell update in fp32 registers, h_t back into the other A buffer; each reads its read's next base
+// straight from the caller's sequence bytes.  One elected lane of a warp-uniform warp issues the MMAs.  The recurrence is pipelined as a wavefront: chunk 0 of step t+1 accumulates K-chunk kc as
 // soon as the activation warps have published the 16 hidden units of K-chunk kc of step t
 // (h_ready[kc]), so the tensor pipe trails the activation pipe by one chunk instead of one step.
 //
-// FAST  : cta_group::1, one fp16 pass (9 MMAs of 128x64x16 per chunk), tanh.approx activations.
+// FAST  : cta_group::1, one fp16 pass (9 MMAs of 128x128x16 per chunk), tanh.approx activations.
 // EXACT : cta_group::2 — a CTA pair shares the weights (each SM holds half of the N columns of
 //         W_hi and W_lo: 136 KB) and runs two tiles (M = 256) in lock step; three fp16 passes
-//         W_hi.h_hi + W_lo.h_hi + W_hi.h_lo (25 MMAs per chunk) with fp32 accumulation; ex2/rcp
-//         activations accurate to a few ulp.
+//         W_lo.h_hi + W_hi.h_lo + W_hi.h_hi (25 MMAs per chunk, small products first) with fp32
+//         accumulation; merged-denominator ex2/rcp activations accurate to a few ulp.
 // See DESIGN.md for the layout tables and the roofline arithmetic.
 #include <cuda_fp16.h>
 #include "rd_common.cuh"
