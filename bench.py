@@ -47,6 +47,9 @@ FLOP_PER_READ = 131072 * READ_LEN + 1024          # n*2*128*512 
 METRIC = "reads/sec classified (100 bp)"
 
 
+OUT = sys.stdout        # main() points this at the real stdout and sends everything else on fd 1 to stderr
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -149,7 +152,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -308,7 +311,7 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": threads, "kind": "port",
                                     "sample": sample,
                                     "note": "ORT unavailable - torch-CPU stand-in for ribodetector_cpu"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     model.close()
     if world > 1:
         dist.destroy_process_group()
@@ -334,7 +337,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the ONE JSON line (NCCL's version banner)
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, forked
+    # workers) are sent to stderr instead
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -275,6 +275,54 @@ class Predictor:
 
     run_with_chunks = run
 
+    # ---- detect.py:586-663, for code that drives the model batch by batch like the reference loop ----------
+    @staticmethod
+    def generate_chunks(reads, n):
+        for i in range(0, len(reads), n):
+            yield reads[i:i + n]
+
+    @staticmethod
+    def generate_paired_read_chunks(reads, n):
+        r1, r2 = reads
+        for i in range(0, len(r1), n):
+            yield r1[i:i + n], r2[i:i + n]
+
+    @staticmethod
+    def separate_reads(reads, labels):
+        from collections import defaultdict
+        reads_dict = defaultdict(list)
+        for read, label in zip(reads, labels):
+            reads_dict[int(label)].append(read)
+        return reads_dict
+
+    def separate_paired_reads(self, r1_reads, r1_outs, r2_reads, r2_outs):
+        """Pair rule of `-e` on the two ends' logits (rd_pair_combine on the device), then routing."""
+        from collections import defaultdict
+        labels = self.model.pair_combine(r1_outs, r2_outs, self.args.ensure).cpu().tolist()
+        r1_dict, r2_dict = defaultdict(list), defaultdict(list)
+        for r1, r2, label in zip(r1_reads, r2_reads, labels):
+            r1_dict[label].append(r1)
+            r2_dict[label].append(r2)
+        return r1_dict, r2_dict
+
+
+# ---- the reference's feed contract (detect.py:666-726), kept for code written against it ------------------
+def unlabeled_read_collate_fn(batch, max_len=100, pack_seq=True):
+    """batch of record tuples → (list of record texts, ReadBatch).  Same signature as the reference;
+    the encoded data is the byte form the CUDA path consumes instead of a PackedSequence of one-hot rows."""
+    from .model import ReadBatch
+    read_list = ['\n'.join(read) for read in batch]
+    seqs = [read[1][:max_len].encode("latin-1") for read in batch]
+    off = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    return read_list, ReadBatch(np.frombuffer(b"".join(seqs), np.uint8).copy(), off, max_len, pack_seq)
+
+
+def unlabeled_paired_read_collate_fn(batch, max_len=100, pack_seq=True):
+    r1_list, r1_data = unlabeled_read_collate_fn([p[0] for p in batch], max_len, pack_seq)
+    r2_list, r2_data = unlabeled_read_collate_fn([p[1] for p in batch], max_len, pack_seq)
+    return r1_list, r1_data, r2_list, r2_data
+
 
 def build_parser(gpu=True):
     args = argparse.ArgumentParser(description='rRNA sequence detector', formatter_class=RawTextHelpFormatter)

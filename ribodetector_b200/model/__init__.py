@@ -1,1 +1,1 @@
-from .model import SeqModel  # noqa: F401
+from .model import SeqModel, ReadBatch  # noqa: F401

@@ -34,6 +34,25 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+class ReadBatch:
+    """What the collate functions hand to the model in place of the reference's PackedSequence of one-hot
+    rows (detect.py:685): the sequence bytes of a batch, already cut to `max_len`, plus offsets.
+    ``.to(device)`` mirrors the reference loop's ``data.to(self.device, non_blocking=True)``."""
+
+    def __init__(self, seq, off, max_len, pack_seq=True):
+        self.seq, self.off, self.max_len, self.pack_seq = torch.as_tensor(seq), torch.as_tensor(off), int(max_len), bool(pack_seq)
+
+    def to(self, device, non_blocking=False):
+        return ReadBatch(self.seq.to(device, non_blocking=non_blocking), self.off.to(device, non_blocking=non_blocking),
+                         self.max_len, self.pack_seq)
+
+    def pin_memory(self):
+        return ReadBatch(self.seq.pin_memory(), self.off.pin_memory(), self.max_len, self.pack_seq)
+
+    def __len__(self):
+        return self.off.numel() - 1
+
+
 class SeqModel:
     """BiLSTM(4→128) + Linear(256→2) classifier.  ``model(x)`` returns raw logits ``[B, 2]``."""
 
@@ -284,10 +303,13 @@ class SeqModel:
     _ALPHABET = None
 
     def __call__(self, x):
-        """x: PackedSequence of one-hot rows (detect.py:685) → packed semantics, or a padded
+        """x: a ReadBatch (this package's collate output), a PackedSequence of one-hot rows (detect.py:685) → packed semantics, or a padded
         one-hot tensor [B, T, 4] (detect.py:687 / detect_cpu.py:699-700) → padded semantics.
         One-hot rows are turned back into base bytes on the device (plumbing only)."""
         self._need()
+        if isinstance(x, ReadBatch):
+            return self.classify(x.seq, x.off, x.max_len, semantics="packed" if x.pack_seq else "padded",
+                                 want_labels=False)[0]
         if isinstance(x, PackedSequence):
             padded, lens = pad_packed_sequence(x.to(self._device), batch_first=True)
             semantics = "packed"

@@ -378,3 +378,39 @@ def test_cli_rejects_bad_file_counts(tmp_path):
     (tmp_path / "a.txt").write_text("@r\nACGT\n+\nIIII\n")
     with pytest.raises(ValueError):                      # unknown extension, like seq_encoder.py:35-37
         detect.main(["-l", "100", "-i", str(tmp_path / "a.txt"), "-o", str(tmp_path / "o.fq")])
+
+
+# ---- the reference's module-level surface (same names) ---------------------------------------------------
+def test_reference_named_encoders_and_loaders(gpu_model, tmp_path):
+    from ribodetector_b200.data_loader import seq_encoder, seq_parser
+    g = load_golden("encode")
+    reads = split_reads(g["seq"], g["off"])
+    for r in reads[:12]:
+        assert np.array_equal(seq_encoder.encode_read(r).cpu().numpy(), encoders.encode_read(r))
+        assert np.array_equal(seq_encoder.encode_variable_len_read(r, 16).cpu().numpy(), encoders.encode_variable_len_read(r, 16))
+    assert seq_encoder.BASE_DICT["U"] == seq_encoder.BASE_DICT["T"] == (0, 0, 0, 1) and seq_encoder.ZERO_LIST == (0, 0, 0, 0)
+    p = tmp_path / "x.fq"
+    p.write_text("@a\nACGT\n+\nIIII\n@b\nGG\n+\n##\n")
+    assert seq_encoder.load_reads(str(p)) == [("@a", "ACGT", "+", "IIII"), ("@b", "GG", "+", "##")]
+    assert [len(c) for c in seq_encoder.get_seq_chunks(str(p), 1)] == [1, 1]
+    with open(p) as fh:
+        assert list(seq_parser(fh, "fastq")) == seq_encoder.load_reads(str(p))
+
+
+def test_reference_style_batch_loop(gpu_model):
+    """The loop of detect.py:284-290 written against this package: collate → model(data.to(device)) → argmax."""
+    from ribodetector_b200.detect import unlabeled_read_collate_fn, unlabeled_paired_read_collate_fn, Predictor
+    g = load_golden("se_L100")
+    reads = split_reads(g["seq"], g["off"])
+    batch = [("@r%d" % i, r, "+", "I" * len(r)) for i, r in enumerate(reads) if r]
+    keep = [i for i, r in enumerate(reads) if r]
+    texts, data = unlabeled_read_collate_fn(batch, max_len=100, pack_seq=True)
+    out = gpu_model(data.to("cuda", non_blocking=True))
+    check_logits(out.cpu().numpy(), g["logits_packed"][keep], "tc_exact")
+    labels = torch.argmax(out, dim=1).tolist()
+    sep = Predictor.separate_reads(texts, labels)
+    assert len(sep[0]) + len(sep[1]) == len(batch) and sep[0][0].count("\n") == 3
+    texts, data = unlabeled_read_collate_fn(batch, max_len=100, pack_seq=False)
+    check_logits(gpu_model(data.to("cuda")).cpu().numpy(), g["logits_padded"][keep], "tc_exact")
+    r1l, r1d, r2l, r2d = unlabeled_paired_read_collate_fn(list(zip(batch[:50], batch[50:100])), 100, True)
+    assert len(r1l) == len(r2l) == 50 and len(r1d) == len(r2d) == 50
