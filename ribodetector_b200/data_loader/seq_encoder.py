@@ -39,7 +39,7 @@ def _encoder():
 
 
 def _bytes(seq):
-    return np.frombuffer(seq.encode("latin-1") if isinstance(seq, str) else bytes(seq), np.uint8)
+    return np.frombuffer(seq.encode("latin-1") if isinstance(seq, str) else bytes(seq), np.uint8).copy()
 
 
 def encode_read(read):
