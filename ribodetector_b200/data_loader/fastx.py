@@ -40,10 +40,44 @@ and followed by ".gz" or ".gzip" if they are gzipped.""".format(ext))
     return ("fa" if ext in FA_EXTS else "fq") + encoding
 
 
-def open_for_write(read_file):
+class ParallelGzipWriter:
+    """gzip level 5 like the reference's open_for_write (detect.py:729-741), but every write() is cut into
+    blocks that are deflated on `threads` threads (zlib releases the GIL) and appended as separate gzip
+    members.  A multi-member file is a valid .gz: gzip / zcat / Python's gzip read back the identical
+    text; the reference's single-threaded writer is what makes it "2 times slower to write gz files"."""
+
+    BLOCK = 8 << 20
+
+    def __init__(self, path, threads=4, compresslevel=5):
+        from concurrent.futures import ThreadPoolExecutor
+        self.fh = open(path, "wb")
+        self.level = compresslevel
+        self.pool = ThreadPoolExecutor(max(1, int(threads)))
+
+    def write(self, data):
+        mv = memoryview(data).cast("B")
+        blocks = [mv[i:i + self.BLOCK] for i in range(0, len(mv), self.BLOCK)]
+        for z in self.pool.map(lambda b: gzip.compress(b, self.level), blocks):
+            self.fh.write(z)
+        return len(mv)
+
+    def close(self):
+        if self.fh.tell() == 0:
+            self.fh.write(gzip.compress(b"", self.level))     # an empty but valid gzip file
+        self.fh.close()
+        self.pool.shutdown()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def open_for_write(read_file, threads=4):
     """Binary twin of detect.py:729-741: gzip level 5 for names ending in 'gz', plain otherwise."""
     if read_file.endswith("gz"):
-        return gzip.open(read_file, mode="wb", compresslevel=5)
+        return ParallelGzipWriter(read_file, threads)
     return open(read_file, "wb")
 
 

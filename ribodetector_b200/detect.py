@@ -182,12 +182,12 @@ class Predictor:
                 colors.OKBLUE, ", ".join(self.rrna), colors.ENDC))
         self.logger.info('Writing output non-rRNA sequences into file: {}{}{}'.format(
             colors.OKBLUE, ", ".join(self.output), colors.ENDC))
-        fh_non = [open_for_write(f) for f in self.output]
-        fh_rrna = [open_for_write(f) for f in self.rrna] if self.rrna is not None else None
+        fh_non = [open_for_write(f, threads) for f in self.output]
+        fh_rrna = [open_for_write(f, threads) for f in self.rrna] if self.rrna is not None else None
         fh_unc = None
         if want_unc:
             unc = [f + '.unclassified.gz' for f in self.output]
-            fh_unc = [open_for_write(f) for f in unc]
+            fh_unc = [open_for_write(f, threads) for f in unc]
             self.logger.info('Writing unclassified sequences into file: {}{}{}'.format(
                 colors.OKYELLOW, ", ".join(unc), colors.ENDC))
 
