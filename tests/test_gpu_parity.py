@@ -414,3 +414,34 @@ def test_reference_style_batch_loop(gpu_model):
     check_logits(gpu_model(data.to("cuda")).cpu().numpy(), g["logits_padded"][keep], "tc_exact")
     r1l, r1d, r2l, r2d = unlabeled_paired_read_collate_fn(list(zip(batch[:50], batch[50:100])), 100, True)
     assert len(r1l) == len(r2l) == 50 and len(r1d) == len(r2d) == 50
+
+
+def test_bitwise_determinism_and_batch_independence(gpu_model):
+    """Same reads → same bits, run to run and whatever else is in the batch (no atomics on the data path;
+    a read's tile-mates and the CTA that runs it do not change its result)."""
+    seq, off = synth.synth_reads(30000, 30, 150, 77)
+    for prec in built_precisions(gpu_model):
+        a = gpu_model.classify(seq, off, 120, precision=prec)[0].cpu().numpy()
+        b = gpu_model.classify(seq, off, 120, precision=prec)[0].cpu().numpy()
+        assert np.array_equal(a, b)
+        sub_off = off[:5001]
+        c = gpu_model.classify(seq[:sub_off[-1]], sub_off, 120, precision=prec)[0].cpu().numpy()
+        assert np.array_equal(a[:5000], c)
+
+
+def test_saturating_and_repetitive_reads(gpu_model, numpy_oracle):
+    """Homopolymers, short tandem repeats and all-N runs at 300 steps: gates sit in saturation for hundreds of
+    steps (exercises the exponent clamps of the exact cell and the zero-row input)."""
+    reads = []
+    for base in "ACGTN":
+        reads += [base * 300, base * 37]
+    for unit in ("AC", "GT", "ACG", "TTAGGG", "CAG", "AT"):
+        reads += [(unit * 200)[:300], (unit * 200)[:123]]
+    reads += ["A" * 150 + "N" * 150, "N" * 150 + "C" * 150, "ACGT" * 10 + "N" * 200 + "ACGT" * 10]
+    seq, off = encoders.flatten_reads(reads)
+    for sem in ("packed", "padded"):
+        ref = numpy_oracle.logits(reads, 300, sem)
+        for prec in built_precisions(gpu_model):
+            got = gpu_model.classify(seq, off, 300, semantics=sem, precision=prec)[0].cpu().numpy()
+            assert np.isfinite(got).all()
+            check_logits(got, ref, prec, 300)
