@@ -1,5 +1,8 @@
+"""Error of the three precisions against the fp64 oracle as a function of read length (run on the B200 box:
+python tests/len_err_report.py).  Lives under tests/ because it uses the oracle."""
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ribodetector_b200.model import SeqModel
 from ribodetector_b200.utils import synth
 from ribodetector_b200.utils.weights import load_weights

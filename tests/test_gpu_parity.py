@@ -8,7 +8,7 @@ Tolerances (stated once, used everywhere):
     reference margin |l1-l0| > 4e-4 (= 2 x eps), the in-band count is asserted small.  The bound
     is for reads of up to 100 steps and scales linearly with -l beyond that (rounding drift of a
     recurrence grows with its length: torch-CPU fp32 itself moves from 7e-6 at 100 bp to 3e-5 at
-    300 bp against the fp64 restatement; tc_exact measures 1.5e-5 / 9e-5, tools/len_err.py)
+    300 bp against the fp64 restatement; tc_exact measures 1.5e-5 / 9e-5, tests/len_err_report.py)
   * precision tc_fast: |dlogit| <= 5e-2, |dp| <= 2e-2, flip rate reported/asserted < 0.1 %
 """
 import numpy as np
