@@ -58,6 +58,11 @@ typedef struct rd_handle rd_handle;
 #define RD_PREC_FP32     0
 #define RD_PREC_TC_EXACT 1
 #define RD_PREC_TC_FAST  2
+/*   TC_AUTO  : two passes — TC_FAST over every read, then TC_EXACT over the reads whose fast margin
+ *              |l1 - l0| is below 0.25 * max(1, max_len/100) (5x the fast mode's logit error bound, ~1 % of
+ *              reads): LABELS equal TC_EXACT's, logits are exact-grade inside the band and fast-grade
+ *              (|dlogit| <= 5e-2 * max(1, max_len/100)) outside it                                    */
+#define RD_PREC_TC_AUTO  3
 
 /* paired-end combination, detect.py:616-663 (`-e/--ensure`) */
 #define RD_PAIR_NONE   0   /* argmax(logits_r1 + logits_r2)            detect.py:655-661 */

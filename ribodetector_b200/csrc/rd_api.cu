@@ -23,8 +23,22 @@ extern "C" int64_t rd_kernel_launches(const rd_handle* h) { return h ? h->launch
 
 static void free_scratch(rd_handle* h) {
     cudaFree(h->d_plan); cudaFree(h->d_splan); cudaFree(h->d_perm); cudaFree(h->d_codes);
+    cudaFree(h->d_splan2); cudaFree(h->d_perm2); cudaFree(h->d_band);
     h->d_plan = h->d_splan = nullptr; h->d_perm = nullptr; h->d_codes = nullptr;
-    h->cap_n = h->cap_slots = h->cap_codes = 0;
+    h->d_splan2 = nullptr; h->d_perm2 = nullptr; h->d_band = nullptr;
+    h->cap_n = h->cap_slots = h->cap_codes = h->cap_band = 0;
+}
+
+static int ensure_band(rd_handle* h) {          // TC_AUTO scratch, sized like the slot tables
+    if (h->cap_band >= h->cap_slots && h->d_perm2) return RD_OK;
+    RD_CUDA(h, cudaDeviceSynchronize());
+    cudaFree(h->d_splan2); cudaFree(h->d_perm2); cudaFree(h->d_band);
+    h->d_splan2 = nullptr; h->d_perm2 = nullptr; h->d_band = nullptr;
+    RD_CUDA(h, cudaMalloc(&h->d_splan2, sizeof(uint32_t) * (h->cap_slots + 2 * RD_TILE)));
+    RD_CUDA(h, cudaMalloc(&h->d_perm2, sizeof(int32_t) * (h->cap_slots + 2 * RD_TILE)));
+    RD_CUDA(h, cudaMalloc(&h->d_band, sizeof(int64_t) * (h->cap_slots / 256 + 4)));
+    h->cap_band = h->cap_slots;
+    return RD_OK;
 }
 
 static int ensure_scratch(rd_handle* h, int64_t n, int max_len, bool need_codes = false) {
@@ -233,7 +247,16 @@ static int classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_
     {
         StageTimer tm(h, 1, st);
         if (precision == RD_PREC_FP32) rc = rd_launch_lstm_simt(h, tiles, max_len, d_logits, st);
-        else rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, precision, d_logits, st);
+        else if (precision == RD_PREC_TC_AUTO) {
+            // fast pass over everything, exact pass over the low-margin reads (their count stays on the device)
+            rc = ensure_band(h);
+            if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_FAST, d_logits, st);
+            const float tau = 0.25f * (max_len > 100 ? (float)max_len / 100.0f : 1.0f);
+            if (!rc) rc = rd_launch_band_select(h, d_logits, tiles, tau, st);
+            const int64_t nb = (tiles * RD_TILE + 255) / 256;
+            if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_EXACT, d_logits, st, h->d_splan2,
+                                            h->d_perm2, h->d_band + nb);
+        } else rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, precision, d_logits, st);
     }
     if (rc) return rc;
     if (d_probs || d_labels || d_counts) {
@@ -251,7 +274,7 @@ extern "C" int rd_classify(rd_handle* h, const uint8_t* d_seq, const int64_t* d_
     if (rc) return rc;
     if (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED)
         return fail(h, RD_ERR_INVALID, "rd_classify: unknown semantics");
-    if (precision < RD_PREC_FP32 || precision > RD_PREC_TC_FAST)
+    if (precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO)
         return fail(h, RD_ERR_INVALID, "rd_classify: unknown precision");
     if (n == 0) return RD_OK;
     if (!d_off || !d_logits) return fail(h, RD_ERR_INVALID, "rd_classify: d_off and d_logits are required");
@@ -318,7 +341,7 @@ static int classify_host_impl(rd_handle* h, int ends,
     if (rc) return rc;
     if (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED)
         return fail(h, RD_ERR_INVALID, "rd_classify_host: unknown semantics");
-    if (precision < RD_PREC_FP32 || precision > RD_PREC_TC_FAST)
+    if (precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO)
         return fail(h, RD_ERR_INVALID, "rd_classify_host: unknown precision");
     if (ends == 2 && (mode < RD_PAIR_NONE || mode > RD_PAIR_BOTH))
         return fail(h, RD_ERR_INVALID, "rd_classify_pairs_host: unknown mode");

@@ -66,6 +66,10 @@ struct rd_handle {
     uint32_t* d_plan = nullptr;
     uint32_t* d_splan = nullptr;
     int32_t* d_perm = nullptr;
+    uint32_t* d_splan2 = nullptr;  // TC_AUTO: the slots of the reads re-run in exact mode (same order, compacted)
+    int32_t* d_perm2 = nullptr;
+    int64_t* d_band = nullptr;     // [slots/256 + 2]: per-block band counts -> exclusive offsets; last = total
+    int64_t cap_band = 0;
     uint8_t* d_codes = nullptr;
     int32_t* d_hist = nullptr;     // [RD_MAX_LEN+2] histogram → bucket starts
     int32_t* d_cursor = nullptr;   // [RD_MAX_LEN+2]
@@ -111,7 +115,9 @@ int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, i
                      int layout, float* d_out, int64_t* d_row_off, cudaStream_t st);
 int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int max_len, float* d_logits, cudaStream_t st);
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
-                      int precision, float* d_logits, cudaStream_t st);
+                      int precision, float* d_logits, cudaStream_t st, const uint32_t* d_splan = nullptr,
+                      const int32_t* d_perm = nullptr, const int64_t* d_n_reads = nullptr);
+int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st);
 int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_probs, int8_t* d_labels,
                    int64_t* d_counts, cudaStream_t st);
 int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n, int mode,

@@ -299,7 +299,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <bool EXACT, int G>
 __global__ void __launch_bounds__(tc_threads(G), 1)
 lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,   // the caller's reads
-               const uint32_t* __restrict__ splan, const int32_t* __restrict__ perm, int L, int n_tiles,
+               const uint32_t* __restrict__ splan, const int32_t* __restrict__ perm, int L, int n_tiles_arg,
+               const int64_t* __restrict__ n_reads_dev,   // non-NULL: the slot count lives on the device (TC_AUTO)
                const uint8_t* __restrict__ img_hi,     // [CG][HI_BYTES] weight images (rd_tc_create)
                const uint8_t* __restrict__ img_lo,     // [CG][LO_BYTES]
                const float* __restrict__ wout,         // [2][256]
@@ -323,6 +324,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = n_reads_dev ? (int)((*n_reads_dev + RD_TILE - 1) / RD_TILE) : n_tiles_arg;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;      // a unit = one CTA (pair)
 
@@ -719,8 +721,11 @@ void rd_tc_destroy(rd_handle* h) {
 }
 
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int L, int precision,
-                      float* d_logits, cudaStream_t st) {
-    if (n_tiles == 0) return RD_OK;
+                      float* d_logits, cudaStream_t st, const uint32_t* d_splan, const int32_t* d_perm,
+                      const int64_t* d_n_reads) {
+    if (n_tiles == 0) return RD_OK;            // (with d_n_reads: an upper bound used to size the grid)
+    if (!d_splan) d_splan = h->d_splan;
+    if (!d_perm) d_perm = h->d_perm;
     rd_tc_state* s = h->tc;
     if (!s) { h->err = "tensor-core state missing"; return RD_ERR_UNSUPPORTED; }
     if (precision == RD_PREC_TC_FAST) {
@@ -731,7 +736,7 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
         }
         int grid = (int)(n_tiles < h->sm_count ? n_tiles : h->sm_count);
         lstm_tc_kernel<false, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
-            d_seq, d_off, h->d_splan, h->d_perm, L, (int)n_tiles, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
+            d_seq, d_off, d_splan, d_perm, L, (int)n_tiles, d_n_reads, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
             h->d_revlut, d_logits);
     } else {
         using C = Cfg<true>;
@@ -751,11 +756,11 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        const uint32_t* splan = h->d_splan; const int32_t* perm = h->d_perm;
+        const uint32_t* splan = d_splan; const int32_t* perm = d_perm;
         int nt = (int)n_tiles;
         const uint8_t* ihi = s->d_img_hi; const uint8_t* ilo = s->d_img_lo;
         const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
-        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, d_seq, d_off, splan, perm, L, nt, ihi, ilo, wout, bout, lut,
+        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, d_seq, d_off, splan, perm, L, nt, d_n_reads, ihi, ilo, wout, bout, lut,
                                       d_logits));
     }
     h->launches += 1;

@@ -107,6 +107,83 @@ reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [128][512]
     }
 }
 
+// ---- TC_AUTO: order-preserving compaction of the slots whose fast-pass margin is inside the band -------------
+// (slots are sorted by step count; keeping their order keeps the compacted tiles length-bucketed)
+__device__ __forceinline__ bool in_band(const int32_t* perm, const float2* logits, int64_t s, float tau) {
+    const int32_t rd = perm[s];
+    if (rd < 0) return false;
+    const float2 l = logits[rd];
+    return fabsf(l.y - l.x) < tau;                        // NaN (invalid read) compares false
+}
+
+__global__ void __launch_bounds__(256)
+band_count_kernel(const int32_t* __restrict__ perm, const float2* __restrict__ logits, int64_t slots, float tau,
+                  int64_t* __restrict__ band) {
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool f = s < slots && in_band(perm, logits, s, tau);
+    const int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) band[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+band_scan_kernel(int64_t* __restrict__ band, int64_t nb) {          // exclusive scan in place; band[nb] = total
+    __shared__ int64_t part[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < nb ? band[i] : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            const int64_t a = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+            __syncthreads();
+            part[threadIdx.x] += a;
+            __syncthreads();
+        }
+        if (i < nb) band[i] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += part[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) band[nb] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+band_write_kernel(const int32_t* __restrict__ perm, const uint32_t* __restrict__ splan, const float2* __restrict__ logits,
+                  int64_t slots, float tau, const int64_t* __restrict__ band, int32_t* __restrict__ perm2,
+                  uint32_t* __restrict__ splan2) {
+    __shared__ int warp_cnt[8];
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool f = s < slots && in_band(perm, logits, s, tau);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[w] = __popc(m);
+    __syncthreads();
+    int before = 0;
+    for (int i = 0; i < w; ++i) before += warp_cnt[i];
+    if (f) {
+        const int64_t dst = band[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+        perm2[dst] = perm[s];
+        splan2[dst] = splan[s];
+    }
+}
+
+int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st) {
+    const int64_t slots = n_tiles * RD_TILE;
+    const int64_t nb = (slots + 255) / 256;
+    RD_CUDA(h, cudaMemsetAsync(h->d_perm2, 0xFF, sizeof(int32_t) * (slots + 2 * RD_TILE), st));   // pad slots: no read
+    RD_CUDA(h, cudaMemsetAsync(h->d_splan2, 0, sizeof(uint32_t) * (slots + 2 * RD_TILE), st));
+    const float2* lg = reinterpret_cast<const float2*>(d_logits);
+    band_count_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, lg, slots, tau, h->d_band);
+    band_scan_kernel<<<1, 1024, 0, st>>>(h->d_band, nb);
+    band_write_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, h->d_splan, lg, slots, tau, h->d_band, h->d_perm2, h->d_splan2);
+    h->launches += 3;
+    RD_CUDA(h, cudaGetLastError());
+    return RD_OK;
+}
+
 int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_probs, int8_t* d_labels,
                    int64_t* d_counts, cudaStream_t st) {
     if (n == 0) return RD_OK;

@@ -445,3 +445,22 @@ def test_saturating_and_repetitive_reads(gpu_model, numpy_oracle):
             got = gpu_model.classify(seq, off, 300, semantics=sem, precision=prec)[0].cpu().numpy()
             assert np.isfinite(got).all()
             check_logits(got, ref, prec, 300)
+
+
+def test_tc_auto_labels_equal_tc_exact(gpu_model):
+    """Two-pass mode: fast everywhere, exact inside the low-margin band → labels identical to tc_exact;
+    logits exact-grade inside the band, fast-grade outside."""
+    for n, L, lo, hi in ((1 << 20, 100, 100, 100), (200000, 300, 40, 300), (1000, 100, 20, 100), (129, 80, 10, 80)):
+        seq, off = synth.synth_reads(n, lo, hi, 4242 + L) if lo != hi else synth.synth_reads_fixed(n, L, 4242)
+        ex, _, lab_ex = gpu_model.classify(seq, off, L, precision="tc_exact")
+        au, _, lab_au = gpu_model.classify(seq, off, L, precision="tc_auto")
+        ex, au = ex.cpu().numpy().astype(np.float64), au.cpu().numpy().astype(np.float64)
+        assert np.array_equal(lab_ex.cpu().numpy(), lab_au.cpu().numpy()), (n, L)
+        tau = 0.25 * max(1.0, L / 100.0)
+        band = np.abs(ex[:, 1] - ex[:, 0]) < 0.8 * tau          # surely re-run in exact mode
+        assert np.array_equal(au[band], ex[band])
+        scale = max(1.0, L / 100.0)
+        assert np.abs(au - ex).max() <= TOL["tc_fast"][0] * scale
+        print("tc_auto n=%d L=%d: %.2f %% of reads inside the band" % (n, L, 100.0 * band.mean()))
+    r = gpu_model.classify_host(seq, off, 80, precision="tc_auto")
+    assert int(r["counts"].sum()) == n
