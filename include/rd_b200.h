@@ -52,9 +52,10 @@ typedef struct rd_handle rd_handle;
 
 /* arithmetic of the forward-direction recurrent contraction
  *   FP32     : fp32 FFMA on CUDA cores, accurate exp/tanh — the on-device fp32 reference
- *   TC_EXACT : tcgen05 kind::f16, fp16 hi/lo split of W_hh and h_t (3 MMA passes, fp32
- *              accumulate in TMEM), fp32 activations
- *   TC_FAST  : tcgen05 kind::f16, single pass, approximate activations                       */
+ *   TC_EXACT : tcgen05 kind::f16 (cta_group::2), fp16 hi/lo split of W_hh and h_t (3 MMA passes,
+ *              fp32 accumulate in TMEM), ex2/rcp activations accurate to a few ulp:
+ *              |dlogit| <= 2e-4 * max(1, max_len/100) vs the reference's fp32 model (measured 1.5e-5)
+ *   TC_FAST  : tcgen05 kind::f16, single pass, tanh.approx activations: |dlogit| <= 5e-2 * max(1, max_len/100) */
 #define RD_PREC_FP32     0
 #define RD_PREC_TC_EXACT 1
 #define RD_PREC_TC_FAST  2
