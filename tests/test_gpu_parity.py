@@ -464,3 +464,27 @@ def test_tc_auto_labels_equal_tc_exact(gpu_model):
         print("tc_auto n=%d L=%d: %.2f %% of reads inside the band" % (n, L, 100.0 * band.mean()))
     r = gpu_model.classify_host(seq, off, 80, precision="tc_auto")
     assert int(r["counts"].sum()) == n
+
+
+def test_cli_fasta_input_is_uppercased_joined_and_classified(gpu_model, numpy_oracle, tmp_path):
+    """FASTA: the reference parser upper-cases and joins the sequence lines (fastx_parser.py:39-55), so lower-case
+    bases ARE classified (unlike FASTQ, where they encode as zero rows) and records come out as 2 lines."""
+    from ribodetector_b200 import detect
+    n = 2000
+    seq, off = synth.synth_reads(n, 50, 140, 515)
+    reads = synth.to_strings(seq, off)
+    text, recs = "", []
+    for i, s in enumerate(reads):
+        lower = s.lower() if i % 3 == 0 else s
+        text += ">c%d some description\n%s\n%s\n" % (i, lower[:60], lower[60:]) if len(s) > 60 else ">c%d\n%s\n" % (i, lower)
+        recs.append((">c%d some description" % i if len(s) > 60 else ">c%d" % i, s.upper()))
+    inp = tmp_path / "in.fasta"
+    inp.write_text(text)
+    out, rr = tmp_path / "non.fa", tmp_path / "rrna.fa"
+    pred = detect.main(["-l", "100", "-i", str(inp), "-o", str(out), "-r", str(rr)])
+    ref = numpy_oracle.logits([r[1] for r in recs], 100, "packed")
+    assert np.abs(ref[:, 1] - ref[:, 0]).min() > 4e-4
+    lab = pairs.argmax_labels(ref)
+    want = _expected_files(recs, lab)
+    assert out.read_text() == want[0] and rr.read_text() == want[1]
+    assert pred.num_seqs == n and pred.num_rrna == int((lab == 1).sum())
