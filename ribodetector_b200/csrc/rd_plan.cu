@@ -295,8 +295,11 @@ int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int
     RD_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int32_t) * (RD_MAX_LEN + 2), st));
     RD_CUDA(h, cudaMemsetAsync(h->d_cursor, 0, sizeof(int32_t) * (RD_MAX_LEN + 2), st));
     RD_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(int32_t) * 8, st));
-    RD_CUDA(h, cudaMemsetAsync(h->d_perm, 0xFF, sizeof(int32_t) * tiles * RD_TILE, st));
-    RD_CUDA(h, cudaMemsetAsync(h->d_splan, 0, sizeof(uint32_t) * tiles * RD_TILE, st));
+    // the scatter fills slots [0, n) exactly (the buckets partition them); only the pad slots of the last
+    // tile (and the pad tile the CTA-pair kernel may touch) need "no read" entries
+    const int64_t pad = (tiles + 1) * RD_TILE - n;
+    RD_CUDA(h, cudaMemsetAsync(h->d_perm + n, 0xFF, sizeof(int32_t) * pad, st));
+    RD_CUDA(h, cudaMemsetAsync(h->d_splan + n, 0, sizeof(uint32_t) * pad, st));
     unsigned nb = (unsigned)((n + 255) / 256);
     plan_kernel<<<nb, 256, 0, st>>>(d_seq, d_off, n, L, semantics, h->d_plan, h->d_hist, h->d_ctrl);
     bucket_scan_kernel<<<1, 1024, 0, st>>>(h->d_hist, nkeys);

@@ -126,7 +126,8 @@ band_count_kernel(const int32_t* __restrict__ perm, const float2* __restrict__ l
 }
 
 __global__ void __launch_bounds__(1024)
-band_scan_kernel(int64_t* __restrict__ band, int64_t nb) {          // exclusive scan in place; band[nb] = total
+band_scan_kernel(int64_t* __restrict__ band, int64_t nb, int32_t* __restrict__ perm2,
+                 uint32_t* __restrict__ splan2) {   // exclusive scan in place; band[nb] = total; pads the compacted tables
     __shared__ int64_t part[1024];
     __shared__ int64_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -148,6 +149,10 @@ band_scan_kernel(int64_t* __restrict__ band, int64_t nb) {          // exclusive
         __syncthreads();
     }
     if (threadIdx.x == 0) band[nb] = carry;
+    __syncthreads();
+    // "no read" entries behind the compacted slots: the rest of the last tile plus one pad tile for the CTA pair
+    const int64_t total = carry;
+    if (threadIdx.x < 2 * RD_TILE) { perm2[total + threadIdx.x] = -1; splan2[total + threadIdx.x] = 0u; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -173,11 +178,9 @@ band_write_kernel(const int32_t* __restrict__ perm, const uint32_t* __restrict__
 int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st) {
     const int64_t slots = n_tiles * RD_TILE;
     const int64_t nb = (slots + 255) / 256;
-    RD_CUDA(h, cudaMemsetAsync(h->d_perm2, 0xFF, sizeof(int32_t) * (slots + 2 * RD_TILE), st));   // pad slots: no read
-    RD_CUDA(h, cudaMemsetAsync(h->d_splan2, 0, sizeof(uint32_t) * (slots + 2 * RD_TILE), st));
     const float2* lg = reinterpret_cast<const float2*>(d_logits);
     band_count_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, lg, slots, tau, h->d_band);
-    band_scan_kernel<<<1, 1024, 0, st>>>(h->d_band, nb);
+    band_scan_kernel<<<1, 1024, 0, st>>>(h->d_band, nb, h->d_perm2, h->d_splan2);
     band_write_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, h->d_splan, lg, slots, tau, h->d_band, h->d_perm2, h->d_splan2);
     h->launches += 3;
     RD_CUDA(h, cudaGetLastError());
