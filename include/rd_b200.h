@@ -181,6 +181,43 @@ int rd_partition_records(const uint8_t* buf, int format, int64_t n, const int64_
 
 const char* rd_fastx_last_error(void);
 
+/* ---- the same edges on the device, for uncompressed FASTQ text resident in HBM --------------------------
+ * K0.  Replaces seq_parser's FASTQ branch (fastx_parser.py:15-47) with rd_scan_fastx's semantics: d_buf[0..len)
+ * (16-byte aligned) is scanned in one pass; d_rec receives int64[8] per record = [begin, end) of the header,
+ * sequence, '+' and quality lines after rstrip(); d_info (device int64[8]) receives [0] newlines seen,
+ * [1] records n (complete ones, <= max_records), [2] consumed = first byte after record n-1, [4] -1 or
+ * 4 * (first malformed record) + kind (1 blank line, 2 header without '@').  Asynchronous on `stream`. */
+int rd_scan_fastq_device(rd_handle* h, const uint8_t* d_buf, int64_t len, int final_chunk, int64_t max_records,
+                         int64_t* d_rec, int64_t* d_info, void* stream);
+
+/* rd_classify over the sequence lines of a record index: read i = d_buf[d_rec[8i+2] .. d_rec[8i+3]). */
+int rd_classify_records(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n, int max_len,
+                        int semantics, int precision, float* d_logits, float* d_probs, int8_t* d_labels,
+                        int64_t* d_counts, void* stream);
+
+/* K4.  Replaces '\n'.join(record) + separate_reads / separate_paired_reads routing (detect.py:680,601-663):
+ * d_out receives the text of the label-0 records, then the label-1 records, then the label -1 records, each
+ * group in input order; d_sizes3 (device int64[3]) their byte counts.  d_out needs len + 1 bytes. */
+int rd_partition_records_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
+                                const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, void* stream);
+
+/* Streaming form over HOST buffers (what Predictor.run does per chunk, detect.py:284-298 / :183-206): block of
+ * FASTQ text in (one per end), partitioned record text out.  Two slots (0, 1) double-buffer the pipeline
+ * H2D -> K0 -> K1..K3 -> K4 -> D2H on the handle's streams.
+ *   rd_fastq_submit  copies buf1 (and buf2: the mates, ends = 2) to the device, scans them and returns, once n
+ *                    is known, *n_records = complete records taken (the same number from each end),
+ *                    consumed2[e] = bytes of buf_e they cover (cut the next block there), out_bytes2[e] = bytes
+ *                    that will land in out_e; classify, partition and the copies back to out1/out2 (host, capacity
+ *                    len_e + 1) and labels (host int8[n], may be NULL) are left running.
+ *   rd_fastq_collect waits for that slot; sizes6 = {non-rRNA, rRNA, unclassified} text bytes in out1 then out2
+ *                    (laid out in that order), counts3 = records per label.
+ * Calls on one handle come from one thread, except that rd_fastq_collect may run on a second thread. */
+int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
+                    int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
+                    int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records, int64_t* consumed2,
+                    int64_t* out_bytes2);
+int rd_fastq_collect(rd_handle* h, int slot, int64_t* sizes6, int64_t* counts3);
+
 #ifdef __cplusplus
 }
 #endif

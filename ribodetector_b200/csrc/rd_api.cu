@@ -142,6 +142,7 @@ extern "C" void rd_destroy(rd_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     rd_tc_destroy(h);
+    rd_fq_destroy(h);
     free_scratch(h);
     cudaFree(h->d_tab_f); cudaFree(h->d_tab_r); cudaFree(h->d_whh_t); cudaFree(h->d_whh_r_t);
     cudaFree(h->d_wout); cudaFree(h->d_bout); cudaFree(h->d_revlut);
@@ -232,16 +233,16 @@ extern "C" int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int res
     return RD_OK;
 }
 
-static int classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
+int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                            int semantics, int precision, float* d_logits, float* d_probs,
-                           int8_t* d_labels, int64_t* d_counts, cudaStream_t st) {
+                           int8_t* d_labels, int64_t* d_counts, cudaStream_t st, int ostride) {
     const bool need_codes = precision == RD_PREC_FP32;
     int rc = ensure_scratch(h, n, max_len, need_codes);
     if (rc) return rc;
     int64_t tiles = 0;
     {
         StageTimer tm(h, 0, st);
-        rc = rd_launch_plan(h, d_seq, d_off, n, max_len, semantics, need_codes, &tiles, st);
+        rc = rd_launch_plan(h, d_seq, d_off, n, max_len, semantics, need_codes, &tiles, st, ostride);
     }
     if (rc) return rc;
     {
@@ -250,13 +251,13 @@ static int classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_
         else if (precision == RD_PREC_TC_AUTO) {
             // fast pass over everything, exact pass over the low-margin reads (their count stays on the device)
             rc = ensure_band(h);
-            if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_FAST, d_logits, st);
+            if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_FAST, d_logits, st, nullptr, nullptr, nullptr, ostride);
             const float tau = 0.25f * (max_len > 100 ? (float)max_len / 100.0f : 1.0f);
             if (!rc) rc = rd_launch_band_select(h, d_logits, tiles, tau, st);
             const int64_t nb = (tiles * RD_TILE + 255) / 256;
             if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_EXACT, d_logits, st, h->d_splan2,
-                                            h->d_perm2, h->d_band + nb);
-        } else rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, precision, d_logits, st);
+                                            h->d_perm2, h->d_band + nb, ostride);
+        } else rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, precision, d_logits, st, nullptr, nullptr, nullptr, ostride);
     }
     if (rc) return rc;
     if (d_probs || d_labels || d_counts) {
@@ -279,7 +280,7 @@ extern "C" int rd_classify(rd_handle* h, const uint8_t* d_seq, const int64_t* d_
     if (n == 0) return RD_OK;
     if (!d_off || !d_logits) return fail(h, RD_ERR_INVALID, "rd_classify: d_off and d_logits are required");
     RD_CUDA(h, cudaSetDevice(h->device));
-    return classify_device(h, d_seq, d_off, n, max_len, semantics, precision, d_logits, d_probs,
+    return rd_classify_device(h, d_seq, d_off, n, max_len, semantics, precision, d_logits, d_probs,
                            d_labels, d_counts, (cudaStream_t)stream);
 }
 
@@ -298,6 +299,7 @@ extern "C" int rd_pair_combine(rd_handle* h, const float* d_logits1, const float
 // ------------------------------------------------------------------------------------------------
 // host-buffer pipeline: chunk c → stage c % NSTAGE;  H2D (s_in) → kernels (s_cmp) → D2H (s_out)
 static const int64_t CHUNK_READS = (int64_t)1 << 21;      // 2 Mi reads per chunk
+static const int64_t FIRST_CHUNK_READS = (int64_t)1 << 18; // the first chunk is small: its H2D is the only copy no kernel hides
 
 static int ensure_stage(rd_handle* h, int64_t n, int64_t bytes, int ends, bool want_probs) {
     if (n <= h->cap_stage_n && bytes <= h->cap_stage_bytes &&
@@ -360,22 +362,24 @@ static int classify_host_impl(rd_handle* h, int ends,
     RD_CUDA(h, cudaSetDevice(h->device));
 
     const int64_t chunk = std::min<int64_t>(CHUNK_READS, n);
+    std::vector<int64_t> cut;                                  // chunk c = reads [cut[c], cut[c+1])
+    cut.push_back(0);
+    if (n > CHUNK_READS) cut.push_back(FIRST_CHUNK_READS);
+    while (cut.back() < n) cut.push_back(std::min(n, cut.back() + chunk));
     int64_t max_bytes = 0;
     for (int e = 0; e < ends; ++e)
-        for (int64_t s = 0; s < n; s += chunk) {
-            int64_t t = std::min(n, s + chunk);
-            max_bytes = std::max(max_bytes, off[e][t] - off[e][s]);
-        }
+        for (size_t c = 0; c + 1 < cut.size(); ++c)
+            max_bytes = std::max(max_bytes, off[e][cut[c + 1]] - off[e][cut[c]]);
     rc = ensure_stage(h, chunk, max_bytes, ends, probs != nullptr);
     if (rc) return rc;
     rc = ensure_scratch(h, chunk, max_len, precision == RD_PREC_FP32);
     if (rc) return rc;
     RD_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(int64_t) * 4, h->s_cmp));
 
-    int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t nchunks = (int64_t)cut.size() - 1;
     for (int64_t c = 0; c < nchunks; ++c) {
         const int st = (int)(c % rd_handle::NSTAGE);
-        const int64_t s = c * chunk, t = std::min(n, s + chunk), m = t - s;
+        const int64_t s = cut[(size_t)c], t = cut[(size_t)c + 1], m = t - s;
         // stage buffers are free once the D2H of chunk c-NSTAGE has been issued and finished
         if (c >= rd_handle::NSTAGE) RD_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_out[st], 0));
         for (int e = 0; e < ends; ++e) {
@@ -391,13 +395,13 @@ static int classify_host_impl(rd_handle* h, int ends,
         RD_CUDA(h, cudaEventRecord(h->ev_in[st], h->s_in));
         RD_CUDA(h, cudaStreamWaitEvent(h->s_cmp, h->ev_in[st], 0));
         if (ends == 1) {
-            rc = classify_device(h, h->d_stage_seq[0][st], h->d_stage_off[0][st], m, max_len, semantics, precision,
+            rc = rd_classify_device(h, h->d_stage_seq[0][st], h->d_stage_off[0][st], m, max_len, semantics, precision,
                                  h->d_stage_logits[0][st], probs ? h->d_stage_probs[st] : nullptr,
                                  h->d_stage_labels[st], h->d_stage_counts, h->s_cmp);
             if (rc) return rc;
         } else {
             for (int e = 0; e < 2; ++e) {
-                rc = classify_device(h, h->d_stage_seq[e][st], h->d_stage_off[e][st], m, max_len, semantics,
+                rc = rd_classify_device(h, h->d_stage_seq[e][st], h->d_stage_off[e][st], m, max_len, semantics,
                                      precision, h->d_stage_logits[e][st], nullptr, nullptr, nullptr, h->s_cmp);
                 if (rc) return rc;
             }

@@ -30,6 +30,7 @@
 #define PLAN_INVALID(p) (((p) >> 29) & 0x1u)
 
 struct rd_tc_state;                // tensor-core weight images (rd_lstm_tc.cu)
+struct rd_fq_state;                // FASTQ-on-device scratch and streaming slots (rd_fastq_dev.cu)
 
 // BASE_DICT of the reference (seq_encoder.py:11-18): A C G T U -> 0 1 2 3 3; everything else (N, IUPAC,
 // lower case, '-') -> 4 = the zero row
@@ -57,6 +58,7 @@ struct rd_handle {
     float* d_bout = nullptr;       // [2]
     float* d_revlut = nullptr;     // [RD_MAX_LEN][5][2] reverse-half logit contributions
     rd_tc_state* tc = nullptr;
+    rd_fq_state* fq = nullptr;
     bool simt_attr_set = false;
 
     // scratch
@@ -110,13 +112,18 @@ struct rd_handle {
 
 // kernels' host launchers (each returns RD_OK / RD_ERR_*; all async on `st`)
 int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
-                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st);
+                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st, int ostride = 1);
 int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                      int layout, float* d_out, int64_t* d_row_off, cudaStream_t st);
 int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int max_len, float* d_logits, cudaStream_t st);
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
                       int precision, float* d_logits, cudaStream_t st, const uint32_t* d_splan = nullptr,
-                      const int32_t* d_perm = nullptr, const int64_t* d_n_reads = nullptr);
+                      const int32_t* d_perm = nullptr, const int64_t* d_n_reads = nullptr, int ostride = 1);
+// read i of a batch is seq[off[i*ostride] .. off[i*ostride + 1]): ostride = 1 for the caller's off[n+1], 8 for the
+// record index of rd_scan_fastq_device (off = rec + 2: the sequence line of every record)
+int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len, int semantics,
+                       int precision, float* d_logits, float* d_probs, int8_t* d_labels, int64_t* d_counts,
+                       cudaStream_t st, int ostride = 1);      // K1 -> K2 -> K3 on `st`, scratch grown on demand
 int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st);
 int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_probs, int8_t* d_labels,
                    int64_t* d_counts, cudaStream_t st);
@@ -125,3 +132,4 @@ int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n
 int rd_build_reverse_lut(rd_handle* h, const float* d_wout_full, cudaStream_t st);
 int rd_tc_create(rd_handle* h, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh);
 void rd_tc_destroy(rd_handle* h);
+void rd_fq_destroy(rd_handle* h);

@@ -1,0 +1,541 @@
+// rd_fastq_dev.cu — the edges of the path on the device: FASTQ text resident in HBM
+// → record index (K0), labels → label-partitioned record text (K4), and the host-buffer streaming form
+// that chains  H2D → K0 → K1..K3 → K4 → D2H  over two slots.
+//
+// Replaces, for uncompressed FASTQ text,
+//   seq_parser                       ribodetector/data_loader/fastx_parser.py:15-47   (K0)
+//   '\n'.join(record)                ribodetector/detect.py:680,711-712               (K4)
+//   separate_reads / separate_paired_reads routing + fh.write   detect.py:601-663,295-298 (K4)
+// with the semantics rd_scan_fastx / rd_partition_records keep on the host (rd_fastx.cu): lines
+// rstrip()ped, not upper-cased, a truncated final record dropped, blank lines an error.
+//
+// All kernels here are HBM-bound byte/integer work:
+//   K0  nl_index_kernel   one pass over the text: 64 B per thread (4 x 16-B loads), newline ranks from a
+//                         single-pass chained scan (decoupled look-back over 16-KB tiles) → line_end[]
+//       record_kernel     one thread per record: the four [begin, end) line ranges after rstrip → rec[n][8]
+//   K4  part_sum / part_scan / part_copy   per-label exclusive offsets of the record texts, then one warp
+//                         per record writes "hdr\nseq\nplus\nqual\n" into [non-rRNA | rRNA | unclassified]
+// Algorithmic HBM bytes per record of B text bytes: K0 = B + 32 (line ends) + 64 (index), K4 = 2 B + 64 + 1.
+#include <algorithm>
+#include <new>
+#include "rd_common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_TILE = SCAN_THREADS * 64;                 // 16 KB of text per CTA
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
+
+__device__ __forceinline__ bool py_space(uint32_t c) {        // what str.rstrip() removes for ASCII text
+    return c == ' ' || (c >= 0x09u && c <= 0x0du) || (c >= 0x1cu && c <= 0x1fu);
+}
+
+// ---- K0a: newline positions, in order, in one pass -------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+nl_index_kernel(const uint8_t* __restrict__ buf, int64_t len, int64_t ntiles, unsigned long long* desc, int* ticket,
+                int64_t* __restrict__ line_end, int64_t cap, int64_t* __restrict__ info) {
+    __shared__ int64_t s_tile, s_base;
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);               // tiles are taken in launch order: look-back never waits on a CTA that has not started
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t p0 = tile * SCAN_TILE + (int64_t)tid * 64;
+    uint32_t m[16];                                            // 0x01 in every byte that is '\n'
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t pos = p0 + 16 * j;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (pos + 16 <= len) {
+            v = __ldg(reinterpret_cast<const uint4*>(buf + pos));
+        } else if (pos < len) {                                // the text's last, partial 16 bytes
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int b = 0; b < 16; ++b)
+                if (pos + b < len) w[b >> 2] |= (uint32_t)buf[pos + b] << (8 * (b & 3));
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        m[4 * j + 0] = __vcmpeq4(v.x, 0x0A0A0A0Au) & 0x01010101u;
+        m[4 * j + 1] = __vcmpeq4(v.y, 0x0A0A0A0Au) & 0x01010101u;
+        m[4 * j + 2] = __vcmpeq4(v.z, 0x0A0A0A0Au) & 0x01010101u;
+        m[4 * j + 3] = __vcmpeq4(v.w, 0x0A0A0A0Au) & 0x01010101u;
+        cnt += __popc(m[4 * j + 0]) + __popc(m[4 * j + 1]) + __popc(m[4 * j + 2]) + __popc(m[4 * j + 3]);
+    }
+    // exclusive rank of this thread's first newline inside the tile
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int wbase = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const int c = s_warp[w];
+        if (w < warp) wbase += c;
+        tile_total += c;
+    }
+    // chained scan across tiles: publish this tile's aggregate, sum the predecessors' (32 at a time)
+    if (warp == 0) {
+        if (lane == 0) atomicExch(&desc[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)tile_total);
+        int64_t excl = 0;
+        if (tile > 0) {
+            int64_t look = tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                unsigned long long d = ST_INC;                 // before tile 0: inclusive prefix 0
+                if (idx >= 0) {
+                    const volatile unsigned long long* p = desc + idx;
+                    do { d = *p; } while ((d & ST_MASK) == 0ull);
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, (d & ST_MASK) == ST_INC);
+                const int first = inc ? __ffs(inc) - 1 : 32;
+                int64_t v = lane <= first ? (int64_t)(d & ~ST_MASK) : 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                excl += v;
+                if (inc) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(&desc[tile], ST_INC | (unsigned long long)(excl + tile_total));
+        }
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == ntiles - 1) info[0] = excl + tile_total;     // newlines in the whole text
+        }
+    }
+    __syncthreads();
+    int64_t rank = s_base + wbase + (incl - cnt);
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        uint32_t mm = m[w];
+        while (mm) {
+            const int bit = __ffs(mm) - 1;
+            if (rank < cap) line_end[rank] = p0 + 4 * w + (bit >> 3);
+            ++rank;
+            mm &= mm - 1;
+        }
+    }
+}
+
+// ---- K0b: records.  info: [0] newlines (in), [1] records n, [2] consumed bytes, [4] first bad record * 4 + kind
+__global__ void __launch_bounds__(256)
+record_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, int64_t max_records,
+              const int64_t* __restrict__ line_end, int64_t* __restrict__ rec, int64_t* __restrict__ info) {
+    const int64_t n_nl = info[0];
+    const bool open_tail = final_chunk && len > 0 && buf[len - 1] != '\n';      // last line without a newline
+    const int64_t n_lines = n_nl + (open_tail ? 1 : 0);
+    int64_t n = n_lines / 4;                        // a truncated final record is dropped / left for the next block
+    if (n > max_records) n = max_records;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) {
+        info[1] = n;
+        info[2] = n == 0 ? 0 : (4 * n - 1 < n_nl ? line_end[4 * n - 1] + 1 : len);
+    }
+    if (r >= n) return;
+    int64_t v[8];
+    int kind = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t li = 4 * r + k;
+        const int64_t b = li == 0 ? 0 : line_end[li - 1] + 1;
+        int64_t x = li < n_nl ? line_end[li] : len;
+        while (x > b && py_space(buf[x - 1])) --x;                               // line.rstrip()
+        if (x == b && kind == 0) kind = 1;                                       // blank line: the reference raises IndexError
+        v[2 * k] = b;
+        v[2 * k + 1] = x;
+    }
+    if (kind == 0 && buf[v[0]] != '@') kind = 2;
+    if (kind) atomicMin(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)(r * 4 + kind));
+    longlong2* o = reinterpret_cast<longlong2*>(rec + 8 * r);
+    o[0] = make_longlong2(v[0], v[1]);
+    o[1] = make_longlong2(v[2], v[3]);
+    o[2] = make_longlong2(v[4], v[5]);
+    o[3] = make_longlong2(v[6], v[7]);
+}
+
+// ---- K4: label-partitioned record text ------------------------------------------------------------------
+__device__ __forceinline__ int label_class(int8_t l) { return l == 0 ? 0 : (l == 1 ? 1 : 2); }
+
+__device__ __forceinline__ int rec_text_len(const int64_t* __restrict__ rec, int64_t r) {
+    const longlong2* p = reinterpret_cast<const longlong2*>(rec + 8 * r);
+    const longlong2 a = p[0], b = p[1], c = p[2], d = p[3];
+    return (int)((a.y - a.x) + (b.y - b.x) + (c.y - c.x) + (d.y - d.x)) + 4;
+}
+
+// per 256-record block: text bytes of each class
+__global__ void __launch_bounds__(256)
+part_sum_kernel(const int64_t* __restrict__ rec, const int8_t* __restrict__ labels, int64_t n, int64_t* __restrict__ blocksum) {
+    __shared__ int64_t s[3][8];
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int64_t v[3] = {0, 0, 0};
+    if (r < n) {
+        const int c = label_class(labels[r]);
+        const int l = rec_text_len(rec, r);
+        v[0] = c == 0 ? l : 0; v[1] = c == 1 ? l : 0; v[2] = c == 2 ? l : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
+        if ((threadIdx.x & 31) == 0) s[c][threadIdx.x >> 5] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int64_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s[threadIdx.x][w];
+        blocksum[(int64_t)blockIdx.x * 3 + threadIdx.x] = t;
+    }
+}
+
+// one CTA: exclusive scan of the block sums per class, class bases (non-rRNA | rRNA | unclassified), sizes3
+__global__ void __launch_bounds__(1024)
+part_scan_kernel(int64_t* __restrict__ blocksum, int64_t nblk, int64_t* __restrict__ sizes3) {
+    __shared__ int64_t part[1024];
+    __shared__ int64_t carry[3];
+    const int tid = threadIdx.x;
+    if (tid < 3) carry[tid] = 0;
+    __syncthreads();
+    for (int c = 0; c < 3; ++c) {
+        for (int64_t base = 0; base < nblk; base += 1024) {
+            const int64_t i = base + tid;
+            const int64_t v = i < nblk ? blocksum[i * 3 + c] : 0;
+            part[tid] = v;
+            __syncthreads();
+            for (int d = 1; d < 1024; d <<= 1) {
+                const int64_t o = tid >= d ? part[tid - d] : 0;
+                __syncthreads();
+                part[tid] += o;
+                __syncthreads();
+            }
+            if (i < nblk) blocksum[i * 3 + c] = carry[c] + part[tid] - v;
+            __syncthreads();
+            if (tid == 1023) carry[c] += part[1023];
+            __syncthreads();
+        }
+    }
+    if (tid == 0) { sizes3[0] = carry[0]; sizes3[1] = carry[1]; sizes3[2] = carry[2]; }
+    // class c starts after the classes before it
+    const int64_t b1 = carry[0], b2 = carry[0] + carry[1];
+    for (int64_t i = tid; i < nblk; i += 1024) { blocksum[i * 3 + 1] += b1; blocksum[i * 3 + 2] += b2; }
+}
+
+// 256 records per CTA: in-block exclusive offsets per class, then one warp per record writes its text
+__global__ void __launch_bounds__(256)
+part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ rec, const int8_t* __restrict__ labels,
+                 int64_t n, const int64_t* __restrict__ blockbase, uint8_t* __restrict__ out) {
+    __shared__ int64_t s_dst[256];
+    __shared__ int s_wsum[3][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 256;
+    const int64_t r = r0 + tid;
+    int cls = 0, len = 0;
+    if (r < n) { cls = label_class(labels[r]); len = rec_text_len(rec, r); }
+    int incl[3], mine[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mine[c] = (r < n && cls == c) ? len : 0;
+        int v = mine[c];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += o;
+        }
+        incl[c] = v;
+        if (lane == 31) s_wsum[c][warp] = v;
+    }
+    __syncthreads();
+    if (r < n) {
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_wsum[cls][w];
+        s_dst[tid] = blockbase[(int64_t)blockIdx.x * 3 + cls] + before + (incl[cls] - mine[cls]);
+    }
+    __syncthreads();
+    for (int i = 0; i < 32; ++i) {
+        const int slot = warp * 32 + i;
+        const int64_t rr = r0 + slot;
+        if (rr >= n) break;
+        const longlong2* p = reinterpret_cast<const longlong2*>(rec + 8 * rr);
+        const longlong2 a = p[0], b = p[1], c = p[2], d = p[3];
+        const int t0 = (int)(a.y - a.x) + 1, t1 = t0 + (int)(b.y - b.x) + 1, t2 = t1 + (int)(c.y - c.x) + 1,
+                  t3 = t2 + (int)(d.y - d.x) + 1;
+        uint8_t* o = out + s_dst[slot];
+        for (int j = lane; j < t3; j += 32) {        // output byte j: which line it belongs to, or the '\n' closing one
+            int64_t src; int end;
+            if (j < t0) { src = a.x + j; end = t0; }
+            else if (j < t1) { src = b.x + (j - t0); end = t1; }
+            else if (j < t2) { src = c.x + (j - t1); end = t2; }
+            else { src = d.x + (j - t2); end = t3; }
+            o[j] = j == end - 1 ? (uint8_t)'\n' : buf[src];
+        }
+    }
+}
+
+}  // namespace
+
+// ---- launchers ---------------------------------------------------------------------------------------------
+struct rd_fq_state {
+    static const int NSLOT = 2;
+    // scan scratch (used on s_in only, in order)
+    unsigned long long* d_desc = nullptr; int64_t cap_desc = 0;
+    int* d_ticket = nullptr;
+    int64_t* d_line_end[2] = {nullptr, nullptr}; int64_t cap_lines[2] = {0, 0};
+    // partition scratch (s_cmp only)
+    int64_t* d_blocksum = nullptr; int64_t cap_blk = 0;
+    // streaming slots
+    uint8_t* d_buf[NSLOT][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int64_t cap_buf[NSLOT][2] = {{0, 0}, {0, 0}};
+    uint8_t* d_out[NSLOT][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int64_t cap_out[NSLOT][2] = {{0, 0}, {0, 0}};
+    int64_t* d_rec[NSLOT][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int64_t cap_rec[NSLOT][2] = {{0, 0}, {0, 0}};
+    int8_t* d_labels[NSLOT] = {nullptr, nullptr}; int64_t cap_labels[NSLOT] = {0, 0};
+    float* d_logits[2] = {nullptr, nullptr}; int64_t cap_logits[2] = {0, 0};
+    int64_t* d_info = nullptr;          // [2 ends][8]
+    int64_t* h_info = nullptr;          // pinned mirror + one spare line
+    int64_t* d_res[NSLOT] = {nullptr, nullptr};   // [9]: sizes3 end 0, sizes3 end 1, counts3
+    int64_t* h_res[NSLOT] = {nullptr, nullptr};   // pinned
+    cudaEvent_t ev_cmp[NSLOT] = {nullptr, nullptr}, ev_out[NSLOT] = {nullptr, nullptr};
+    bool pending[NSLOT] = {false, false};
+};
+
+static int fq_state(rd_handle* h, rd_fq_state** out) {
+    if (!h->fq) {
+        rd_fq_state* s = new (std::nothrow) rd_fq_state();
+        if (!s) { h->err = "rd_fastq: out of host memory"; return RD_ERR_NOMEM; }
+        h->fq = s;
+        RD_CUDA(h, cudaMalloc(&s->d_ticket, sizeof(int) * 4));
+        RD_CUDA(h, cudaMalloc(&s->d_info, sizeof(int64_t) * 16));
+        RD_CUDA(h, cudaMallocHost(&s->h_info, sizeof(int64_t) * 24));
+        for (int i = 0; i < rd_fq_state::NSLOT; ++i) {
+            RD_CUDA(h, cudaMalloc(&s->d_res[i], sizeof(int64_t) * 9));
+            RD_CUDA(h, cudaMallocHost(&s->h_res[i], sizeof(int64_t) * 9));
+            RD_CUDA(h, cudaEventCreateWithFlags(&s->ev_cmp[i], cudaEventDisableTiming));
+            RD_CUDA(h, cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    *out = h->fq;
+    return RD_OK;
+}
+
+void rd_fq_destroy(rd_handle* h) {
+    rd_fq_state* s = h->fq;
+    if (!s) return;
+    cudaFree(s->d_desc); cudaFree(s->d_ticket); cudaFree(s->d_blocksum); cudaFree(s->d_info);
+    cudaFreeHost(s->h_info);
+    for (int e = 0; e < 2; ++e) { cudaFree(s->d_line_end[e]); cudaFree(s->d_logits[e]); }
+    for (int i = 0; i < rd_fq_state::NSLOT; ++i) {
+        for (int e = 0; e < 2; ++e) { cudaFree(s->d_buf[i][e]); cudaFree(s->d_out[i][e]); cudaFree(s->d_rec[i][e]); }
+        cudaFree(s->d_labels[i]); cudaFree(s->d_res[i]); cudaFreeHost(s->h_res[i]);
+        if (s->ev_cmp[i]) cudaEventDestroy(s->ev_cmp[i]);
+        if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+    }
+    delete s;
+    h->fq = nullptr;
+}
+
+template <typename T>
+static int grow(rd_handle* h, T** p, int64_t* cap, int64_t want) {       // device buffer of at least `want` elements
+    if (want <= *cap && *p) return RD_OK;
+    RD_CUDA(h, cudaDeviceSynchronize());
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const int64_t n = std::max<int64_t>(want + want / 8, 16);
+    RD_CUDA(h, cudaMalloc(p, sizeof(T) * (size_t)n));
+    *cap = n;
+    return RD_OK;
+}
+
+static int launch_scan(rd_handle* h, rd_fq_state* s, int e, const uint8_t* d_buf, int64_t len, int final_chunk,
+                       int64_t max_records, int64_t* d_rec, int64_t* d_info, cudaStream_t st) {
+    const int64_t ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    int rc = grow(h, &s->d_desc, &s->cap_desc, ntiles);
+    if (!rc) rc = grow(h, &s->d_line_end[e], &s->cap_lines[e], 4 * max_records);
+    if (rc) return rc;
+    RD_CUDA(h, cudaMemsetAsync(d_info, 0, sizeof(int64_t) * 4, st));
+    RD_CUDA(h, cudaMemsetAsync(d_info + 4, 0xFF, sizeof(int64_t), st));            // "no bad record"
+    if (ntiles > 0) {
+        RD_CUDA(h, cudaMemsetAsync(s->d_desc, 0, sizeof(unsigned long long) * ntiles, st));
+        RD_CUDA(h, cudaMemsetAsync(s->d_ticket, 0, sizeof(int), st));
+        nl_index_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(d_buf, len, ntiles, s->d_desc, s->d_ticket,
+                                                                     s->d_line_end[e], 4 * max_records, d_info);
+        h->launches += 1;
+    }
+    const int64_t upper = std::max<int64_t>(1, std::min<int64_t>(max_records, len / 8 + 1));   // a record is >= 8 bytes
+    record_kernel<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(d_buf, len, final_chunk, max_records, s->d_line_end[e],
+                                                                   d_rec, d_info);
+    h->launches += 1;
+    RD_CUDA(h, cudaGetLastError());
+    return RD_OK;
+}
+
+static int launch_partition(rd_handle* h, rd_fq_state* s, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
+                            const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, cudaStream_t st) {
+    if (n == 0) {
+        RD_CUDA(h, cudaMemsetAsync(d_sizes3, 0, sizeof(int64_t) * 3, st));
+        return RD_OK;
+    }
+    const int64_t nblk = (n + 255) / 256;
+    int rc = grow(h, &s->d_blocksum, &s->cap_blk, nblk * 3);
+    if (rc) return rc;
+    part_sum_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_rec, d_labels, n, s->d_blocksum);
+    part_scan_kernel<<<1, 1024, 0, st>>>(s->d_blocksum, nblk, d_sizes3);
+    part_copy_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, d_rec, d_labels, n, s->d_blocksum, d_out);
+    h->launches += 3;
+    RD_CUDA(h, cudaGetLastError());
+    return RD_OK;
+}
+
+static int fq_fail(rd_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+static int parse_error(rd_handle* h, int64_t key) {
+    const int64_t r = key / 4;
+    h->err = (key & 3) == 1 ? "FASTQ: blank line in record " + std::to_string(r) + " (the reference parser raises IndexError here)"
+                            : "FASTQ: record " + std::to_string(r) + " does not start with '@'";
+    return RD_ERR_PARSE;
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+extern "C" int rd_scan_fastq_device(rd_handle* h, const uint8_t* d_buf, int64_t len, int final_chunk, int64_t max_records,
+                                    int64_t* d_rec, int64_t* d_info, void* stream) {
+    if (!h) return RD_ERR_INVALID;
+    if (len < 0 || max_records < 0 || max_records > ((int64_t)1 << 30) || !d_info || (max_records && !d_rec) || (len && !d_buf))
+        return fq_fail(h, RD_ERR_INVALID, "rd_scan_fastq_device: bad arguments");
+    if (((uintptr_t)d_buf & 15) != 0) return fq_fail(h, RD_ERR_INVALID, "rd_scan_fastq_device: d_buf must be 16-byte aligned");
+    RD_CUDA(h, cudaSetDevice(h->device));
+    rd_fq_state* s = nullptr;
+    int rc = fq_state(h, &s);
+    if (rc) return rc;
+    return launch_scan(h, s, 0, d_buf, len, final_chunk, max_records, d_rec, d_info, (cudaStream_t)stream);
+}
+
+extern "C" int rd_classify_records(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n, int max_len,
+                                   int semantics, int precision, float* d_logits, float* d_probs, int8_t* d_labels,
+                                   int64_t* d_counts, void* stream) {
+    if (!h) return RD_ERR_INVALID;
+    if (n < 0 || n > ((int64_t)1 << 30) || max_len < 1 || max_len > RD_MAX_LEN ||
+        (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED) || precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO)
+        return fq_fail(h, RD_ERR_INVALID, "rd_classify_records: bad arguments");
+    if (n == 0) return RD_OK;
+    if (!d_buf || !d_rec || !d_logits) return fq_fail(h, RD_ERR_INVALID, "rd_classify_records: NULL buffer");
+    RD_CUDA(h, cudaSetDevice(h->device));
+    return rd_classify_device(h, d_buf, d_rec + 2, n, max_len, semantics, precision, d_logits, d_probs, d_labels, d_counts,
+                              (cudaStream_t)stream, 8);
+}
+
+extern "C" int rd_partition_records_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
+                                           const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, void* stream) {
+    if (!h) return RD_ERR_INVALID;
+    if (n < 0 || !d_sizes3 || (n && (!d_buf || !d_rec || !d_labels || !d_out)))
+        return fq_fail(h, RD_ERR_INVALID, "rd_partition_records_device: bad arguments");
+    RD_CUDA(h, cudaSetDevice(h->device));
+    rd_fq_state* s = nullptr;
+    int rc = fq_state(h, &s);
+    if (rc) return rc;
+    return launch_partition(h, s, d_buf, d_rec, n, d_labels, d_out, d_sizes3, (cudaStream_t)stream);
+}
+
+extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
+                               int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
+                               int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records,
+                               int64_t* consumed2, int64_t* out_bytes2) {
+    if (!h) return RD_ERR_INVALID;
+    if (slot < 0 || slot >= rd_fq_state::NSLOT || (ends != 1 && ends != 2) || len1 < 0 || (ends == 2 && len2 < 0) ||
+        max_records < 1 || max_records > ((int64_t)1 << 30) || max_len < 1 || max_len > RD_MAX_LEN || !n_records ||
+        !consumed2 || !out_bytes2 || (len1 && !buf1) || (ends == 2 && len2 && !buf2) || !out1 || (ends == 2 && !out2) ||
+        (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED) || precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO ||
+        (ends == 2 && (mode < RD_PAIR_NONE || mode > RD_PAIR_BOTH)))
+        return fq_fail(h, RD_ERR_INVALID, "rd_fastq_submit: bad arguments");
+    RD_CUDA(h, cudaSetDevice(h->device));
+    rd_fq_state* s = nullptr;
+    int rc = fq_state(h, &s);
+    if (rc) return rc;
+    if (s->pending[slot]) return fq_fail(h, RD_ERR_INVALID, "rd_fastq_submit: slot still holds an uncollected block");
+    const uint8_t* bufs[2] = {buf1, buf2};
+    const int64_t lens[2] = {len1, ends == 2 ? len2 : 0};
+    uint8_t* outs[2] = {out1, out2};
+    *n_records = 0;
+    consumed2[0] = consumed2[1] = 0;
+    out_bytes2[0] = out_bytes2[1] = 0;
+    for (int e = 0; e < ends; ++e) {
+        rc = grow(h, &s->d_buf[slot][e], &s->cap_buf[slot][e], lens[e] + 16);
+        if (!rc) rc = grow(h, &s->d_out[slot][e], &s->cap_out[slot][e], lens[e] + 16);
+        if (!rc) rc = grow(h, &s->d_rec[slot][e], &s->cap_rec[slot][e], 8 * max_records);
+        if (!rc) rc = grow(h, &s->d_logits[e], &s->cap_logits[e], 2 * max_records);
+        if (rc) return rc;
+    }
+    rc = grow(h, &s->d_labels[slot], &s->cap_labels[slot], max_records);
+    if (rc) return rc;
+    // H2D + K0 on the copy-in stream; the host needs n and `consumed` before it can cut the next block
+    for (int e = 0; e < ends; ++e) {
+        if (lens[e])
+            RD_CUDA(h, cudaMemcpyAsync(s->d_buf[slot][e], bufs[e], (size_t)lens[e], cudaMemcpyHostToDevice, h->s_in));
+        rc = launch_scan(h, s, e, s->d_buf[slot][e], lens[e], final_chunk, max_records, s->d_rec[slot][e], s->d_info + 8 * e, h->s_in);
+        if (rc) return rc;
+    }
+    RD_CUDA(h, cudaMemcpyAsync(s->h_info, s->d_info, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, h->s_in));
+    RD_CUDA(h, cudaStreamSynchronize(h->s_in));
+    int64_t n = s->h_info[1];
+    if (ends == 2) n = std::min(n, s->h_info[8 + 1]);
+    for (int e = 0; e < ends; ++e) {
+        const int64_t bad = s->h_info[8 * e + 4];
+        if (bad >= 0 && bad / 4 < n) return parse_error(h, bad);
+        consumed2[e] = s->h_info[8 * e + 2];
+    }
+    if (ends == 2)
+        for (int e = 0; e < 2; ++e)
+            if (s->h_info[8 * e + 1] > n) {           // this end holds more records than its mate: give the extra ones back
+                if (n == 0) { consumed2[e] = 0; continue; }
+                RD_CUDA(h, cudaMemcpyAsync(s->h_info + 16, s->d_line_end[e] + (4 * n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->s_in));
+                RD_CUDA(h, cudaStreamSynchronize(h->s_in));
+                consumed2[e] = s->h_info[16] + 1;
+            }
+    *n_records = n;
+    if (n == 0) return RD_OK;
+    rc = rd_reserve(h, n, max_len);
+    if (rc) return rc;
+    // K1..K3 and K4 on the compute stream (everything it reads was completed above)
+    RD_CUDA(h, cudaMemsetAsync(s->d_res[slot], 0, sizeof(int64_t) * 9, h->s_cmp));
+    if (ends == 1) {
+        rc = rd_classify_device(h, s->d_buf[slot][0], s->d_rec[slot][0] + 2, n, max_len, semantics, precision, s->d_logits[0],
+                                nullptr, s->d_labels[slot], s->d_res[slot] + 6, h->s_cmp, 8);
+        if (rc) return rc;
+    } else {
+        for (int e = 0; e < 2; ++e) {
+            rc = rd_classify_device(h, s->d_buf[slot][e], s->d_rec[slot][e] + 2, n, max_len, semantics, precision,
+                                    s->d_logits[e], nullptr, nullptr, nullptr, h->s_cmp, 8);
+            if (rc) return rc;
+        }
+        rc = rd_launch_pair(h, s->d_logits[0], s->d_logits[1], n, mode, s->d_labels[slot], s->d_res[slot] + 6, h->s_cmp);
+        if (rc) return rc;
+    }
+    for (int e = 0; e < ends; ++e) {
+        rc = launch_partition(h, s, s->d_buf[slot][e], s->d_rec[slot][e], n, s->d_labels[slot], s->d_out[slot][e],
+                              s->d_res[slot] + 3 * e, h->s_cmp);
+        if (rc) return rc;
+    }
+    RD_CUDA(h, cudaEventRecord(s->ev_cmp[slot], h->s_cmp));
+    RD_CUDA(h, cudaStreamWaitEvent(h->s_out, s->ev_cmp[slot], 0));
+    for (int e = 0; e < ends; ++e) {
+        // the text of n records is at most the bytes they took in the block (+1: an open last line gains its '\n')
+        out_bytes2[e] = std::min<int64_t>(consumed2[e] + 1, lens[e] + 1);
+        RD_CUDA(h, cudaMemcpyAsync(outs[e], s->d_out[slot][e], (size_t)out_bytes2[e], cudaMemcpyDeviceToHost, h->s_out));
+    }
+    if (labels) RD_CUDA(h, cudaMemcpyAsync(labels, s->d_labels[slot], (size_t)n, cudaMemcpyDeviceToHost, h->s_out));
+    RD_CUDA(h, cudaMemcpyAsync(s->h_res[slot], s->d_res[slot], sizeof(int64_t) * 9, cudaMemcpyDeviceToHost, h->s_out));
+    RD_CUDA(h, cudaEventRecord(s->ev_out[slot], h->s_out));
+    s->pending[slot] = true;
+    return RD_OK;
+}
+
+extern "C" int rd_fastq_collect(rd_handle* h, int slot, int64_t* sizes6, int64_t* counts3) {
+    if (!h) return RD_ERR_INVALID;
+    rd_fq_state* s = h->fq;
+    if (!s || slot < 0 || slot >= rd_fq_state::NSLOT || !s->pending[slot])
+        return RD_ERR_INVALID;                                 // (no message: may run beside rd_fastq_submit on another thread)
+    cudaError_t e = cudaEventSynchronize(s->ev_out[slot]);
+    s->pending[slot] = false;
+    if (e != cudaSuccess) return RD_ERR_CUDA;
+    for (int i = 0; i < 6; ++i) if (sizes6) sizes6[i] = s->h_res[slot][i];
+    for (int i = 0; i < 3; ++i) if (counts3) counts3[i] = s->h_res[slot][6 + i];
+    return RD_OK;
+}

@@ -312,7 +312,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // ---------------------------------------------------------------------------------------------------
 template <bool EXACT, int G>
 __global__ void __launch_bounds__(tc_threads(G), 1)
-lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,   // the caller's reads
+lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int ostride,   // the caller's reads
                const uint32_t* __restrict__ splan, const int32_t* __restrict__ perm, int L, int n_tiles_arg,
                const int64_t* __restrict__ n_reads_dev,   // non-NULL: the slot count lives on the device (TC_AUTO)
                const uint8_t* __restrict__ img_hi,     // [CG][HI_BYTES] weight images (rd_tc_create)
@@ -507,8 +507,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
             // this thread's read: its bytes are consumed one per step straight from the caller's buffer
             // (consecutive steps hit the same 128-B line in L1; HBM sees every base once)
             const int32_t my_rd = have_tile ? perm[slot] : -1;
-            const int64_t my_b = my_rd >= 0 ? off[my_rd] : 0;
-            const int64_t my_l64 = my_rd >= 0 ? off[my_rd + 1] - my_b : 0;
+            const int64_t my_b = my_rd >= 0 ? off[(int64_t)my_rd * ostride] : 0;
+            const int64_t my_l64 = my_rd >= 0 ? off[(int64_t)my_rd * ostride + 1] - my_b : 0;
             const int my_len = (int)(my_l64 < (int64_t)L ? my_l64 : (int64_t)L);
             const uint8_t* cptr = seq + my_b;
             auto code_at = [&](int t) -> uint32_t { return t < my_len ? rd_base_code(__ldg(cptr + t)) : 4u; };
@@ -736,7 +736,7 @@ void rd_tc_destroy(rd_handle* h) {
 
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int L, int precision,
                       float* d_logits, cudaStream_t st, const uint32_t* d_splan, const int32_t* d_perm,
-                      const int64_t* d_n_reads) {
+                      const int64_t* d_n_reads, int ostride) {
     if (n_tiles == 0) return RD_OK;            // (with d_n_reads: an upper bound used to size the grid)
     if (!d_splan) d_splan = h->d_splan;
     if (!d_perm) d_perm = h->d_perm;
@@ -750,7 +750,7 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
         }
         int grid = (int)(n_tiles < h->sm_count ? n_tiles : h->sm_count);
         lstm_tc_kernel<false, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
-            d_seq, d_off, d_splan, d_perm, L, (int)n_tiles, d_n_reads, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
+            d_seq, d_off, ostride, d_splan, d_perm, L, (int)n_tiles, d_n_reads, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
             h->d_revlut, d_logits);
     } else {
         using C = Cfg<true>;
@@ -774,7 +774,7 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
         int nt = (int)n_tiles;
         const uint8_t* ihi = s->d_img_hi; const uint8_t* ilo = s->d_img_lo;
         const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
-        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, d_seq, d_off, splan, perm, L, nt, d_n_reads, ihi, ilo, wout, bout, lut,
+        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, d_seq, d_off, ostride, splan, perm, L, nt, d_n_reads, ihi, ilo, wout, bout, lut,
                                       d_logits));
     }
     h->launches += 1;

@@ -15,13 +15,13 @@ __device__ __forceinline__ uint32_t base_code(uint8_t b) { return rd_base_code(b
 // ---------------------------------------------------------------------------------------------
 // plan: one thread per read
 __global__ void __launch_bounds__(256)
-plan_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int64_t n, int L,
+plan_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int ostride, int64_t n, int L,
             int semantics, uint32_t* __restrict__ plan, int32_t* __restrict__ hist,
             int32_t* __restrict__ ctrl) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int64_t b = off[i];
-    int64_t len64 = off[i + 1] - b;
+    int64_t b = off[i * ostride];                 // read i = seq[off[i*ostride] .. off[i*ostride + 1])
+    int64_t len64 = off[i * ostride + 1] - b;
     int len = (int)(len64 < (int64_t)L ? len64 : (int64_t)L);
     if (len < 0) len = 0;
     uint32_t nfwd, krev, crev, invalid = 0;
@@ -117,7 +117,7 @@ scatter_kernel(const uint32_t* __restrict__ plan, int64_t n, const int32_t* __re
 
 // codes: one CTA per tile; transposes [read][t] bytes into [t][read] code lines via smem
 __global__ void __launch_bounds__(256)
-codes_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
+codes_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int ostride,
              const int32_t* __restrict__ perm, const uint32_t* __restrict__ splan, int L,
              uint8_t* __restrict__ codes) {
     __shared__ __align__(16) uint8_t tile[128][RD_TILE + 4];
@@ -128,8 +128,8 @@ codes_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
     if (tid < RD_TILE) {
         int32_t r = perm[tileid * RD_TILE + tid];
         if (r >= 0) {
-            int64_t b = off[r];
-            int64_t l = off[r + 1] - b;
+            int64_t b = off[(int64_t)r * ostride];
+            int64_t l = off[(int64_t)r * ostride + 1] - b;
             s_beg[tid] = b;
             s_len[tid] = (int)(l < (int64_t)L ? l : (int64_t)L);
         } else {
@@ -287,7 +287,7 @@ onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int L,
-                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st) {
+                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st, int ostride) {
     int64_t tiles = (n + RD_TILE - 1) / RD_TILE;
     *n_tiles_out = tiles;
     if (n == 0) return RD_OK;
@@ -301,13 +301,13 @@ int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int
     RD_CUDA(h, cudaMemsetAsync(h->d_perm + n, 0xFF, sizeof(int32_t) * pad, st));
     RD_CUDA(h, cudaMemsetAsync(h->d_splan + n, 0, sizeof(uint32_t) * pad, st));
     unsigned nb = (unsigned)((n + 255) / 256);
-    plan_kernel<<<nb, 256, 0, st>>>(d_seq, d_off, n, L, semantics, h->d_plan, h->d_hist, h->d_ctrl);
+    plan_kernel<<<nb, 256, 0, st>>>(d_seq, d_off, ostride, n, L, semantics, h->d_plan, h->d_hist, h->d_ctrl);
     bucket_scan_kernel<<<1, 1024, 0, st>>>(h->d_hist, nkeys);
     // keys lie in [0, L]; shared histogram spans L+1 keys
     int kspan = L + 1;
     scatter_kernel<<<nb, 256, sizeof(int32_t) * 2 * kspan, st>>>(h->d_plan, n, h->d_hist, h->d_cursor,
                                                                  h->d_perm, h->d_splan, 0, kspan);
-    if (need_codes) codes_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_seq, d_off, h->d_perm, h->d_splan, L, h->d_codes);
+    if (need_codes) codes_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_seq, d_off, ostride, h->d_perm, h->d_splan, L, h->d_codes);
     h->launches += need_codes ? 4 : 3;
     RD_CUDA(h, cudaGetLastError());
     return RD_OK;

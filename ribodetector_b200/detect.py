@@ -174,8 +174,6 @@ class Predictor:
         from .data_loader import FastxReader, open_for_write, partition_records
         ends = 2 if self.is_paired else 1
         threads = max(1, min(int(self.args.threads), os.cpu_count() or 1))
-        readers = [FastxReader(f, max_records=self.chunk_reads, threads=max(1, threads // ends), pinned=True)
-                   for f in self.input]
         want_unc = self.is_paired and self.args.ensure == 'both'
         if self.rrna is not None:
             self.logger.info('Writing output rRNA sequences into file: {}{}{}'.format(
@@ -191,6 +189,23 @@ class Predictor:
             self.logger.info('Writing unclassified sequences into file: {}{}{}'.format(
                 colors.OKYELLOW, ", ".join(unc), colors.ENDC))
 
+        if self._device_ingest():
+            # FASTQ text goes to the GPU as it is: record scan (K0) and label partition (K4) run there too
+            from .data_loader.fastq_gpu import FastqGpuStream
+            stream = FastqGpuStream(self.models, self.input, self.len, mode=self.args.ensure, semantics=self.semantics,
+                                    precision=self.args.precision, threads=threads)
+            try:
+                total = stream.run({"non": fh_non, "rrna": fh_rrna, "unc": fh_unc})
+            finally:
+                for fh in fh_non + (fh_rrna or []) + (fh_unc or []):
+                    fh.close()
+            self.stage_seconds = stream.stage_seconds
+            self.logger.debug('stage busy seconds: %s', stream.stage_seconds)
+            self._report(stream.num_seqs, total, want_unc)
+            return
+
+        readers = [FastxReader(f, max_records=self.chunk_reads, threads=max(1, threads // ends), pinned=True)
+                   for f in self.input]
         q_in = queue.Queue(maxsize=3)
         q_out = queue.Queue(maxsize=3)
         errors = []
@@ -265,6 +280,16 @@ class Predictor:
         busy["read"] -= sum(r.wait_seconds for r in readers)      # time blocked on buffer back-pressure is not work
         self.stage_seconds = busy
         self.logger.debug('stage busy seconds: %s', busy)
+        self._report(num_seqs, total, want_unc)
+
+    def _device_ingest(self):
+        """FASTQ inputs (plain or gz) take the device ingest path unless --host_ingest asks for the host scanner."""
+        from .data_loader import get_seq_format
+        if getattr(self.args, "host_ingest", False) or self.chunk_size is not None:
+            return False
+        return all(get_seq_format(f).startswith("fq") for f in self.input)
+
+    def _report(self, num_seqs, total, want_unc):
         self.num_seqs, self.num_nonrrna, self.num_rrna, self.num_unknown = num_seqs, int(total[0]), int(total[1]), int(total[2])
         self.logger.info('Processed {}{}{}{} sequences in total'.format(colors.BOLD, colors.OKCYAN, num_seqs, colors.ENDC))
         self.logger.info('Detected {}{}{}{} non-rRNA sequences'.format(colors.BOLD, colors.OKCYAN, self.num_nonrrna, colors.ENDC))
@@ -355,6 +380,9 @@ none: give label based on the mean probability of read pair.
     args.add_argument('--log', default=None, type=str, help='Log file name')
     args.add_argument('--precision', default='tc_exact', choices=['tc_exact', 'tc_auto', 'tc_fast', 'fp32'],
                       help='(extension) arithmetic of the recurrent contraction: tc_exact = tcgen05 3-pass fp16 split,\nfp32-grade logits (default); tc_fast = one fp16 pass; fp32 = CUDA cores')
+    args.add_argument('--host_ingest', action='store_true',
+                      help='(extension) scan FASTQ records and partition the output on the host instead of the GPU\n'
+                           '(FASTA inputs and --chunk_size runs always do)')
     args.add_argument('-v', '--version', action='version', version='%(prog)s {version}'.format(version=__version__))
     return args
 

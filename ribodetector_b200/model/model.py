@@ -299,6 +299,94 @@ class SeqModel:
         _lib.check(self._lib, h, rc, "rd_classify_pairs_host")
         return {"labels": labels, "counts": counts, "logits1": l1, "logits2": l2}
 
+    # ---- FASTQ text on the device (K0 scan, K4 partition) ------------------------------------------
+    def scan_fastq(self, text, final_chunk=True, max_records=None):
+        """FASTQ text (uint8 tensor / bytes; moved to the device) → (d_text, rec int64[n, 8] device tensor of
+        [begin, end) pairs for header / sequence / '+' / quality, n, consumed).  fastx_parser.py:15-47."""
+        h = self._need()
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            text = torch.frombuffer(bytearray(text), dtype=torch.uint8) if len(text) else torch.empty(0, dtype=torch.uint8)
+        text = torch.as_tensor(text)
+        if text.dtype != torch.uint8:
+            raise ValueError("text must be uint8")
+        d_text = text.to(self._device).contiguous()
+        n_bytes = d_text.numel()
+        cap = int(max_records) if max_records is not None else n_bytes // 8 + 1
+        with torch.cuda.device(self._device):
+            rec = torch.empty((max(cap, 1), 8), dtype=torch.int64, device=self._device)
+            info = torch.empty(8, dtype=torch.int64, device=self._device)
+            rc = self._lib.rd_scan_fastq_device(h, _ptr(d_text) if n_bytes else None, n_bytes, int(bool(final_chunk)), cap,
+                                                _ptr(rec), _ptr(info), self._stream())
+        _lib.check(self._lib, h, rc, "rd_scan_fastq_device")
+        info = info.cpu().tolist()
+        n = int(info[1])
+        if info[4] >= 0 and info[4] // 4 < n:
+            raise ValueError("FASTQ: %s in record %d" % ("blank line" if info[4] % 4 == 1 else "header without '@'", info[4] // 4))
+        return d_text, rec[:n], n, int(info[2])
+
+    def classify_records(self, d_text, rec, max_len, semantics=None, precision=None, counts=None):
+        """rd_classify over the sequence lines of a record index → (logits[n,2], labels[n]) on the device."""
+        h = self._need()
+        semantics = semantics or ("packed" if self.pack_seq else "padded")
+        precision = precision or self.precision
+        n = rec.shape[0]
+        with torch.cuda.device(self._device):
+            logits = torch.empty((n, 2), dtype=torch.float32, device=self._device)
+            labels = torch.empty((n,), dtype=torch.int8, device=self._device)
+            rc = self._lib.rd_classify_records(h, _ptr(d_text), _ptr(rec), n, int(max_len), _lib.SEM[semantics],
+                                               _lib.PREC[precision], _ptr(logits), None, _ptr(labels), _ptr(counts),
+                                               self._stream())
+        _lib.check(self._lib, h, rc, "rd_classify_records")
+        return logits, labels
+
+    def partition_records(self, d_text, rec, labels):
+        """labels int8[n] in {0, 1, -1} → (out uint8 device tensor laid out [non-rRNA | rRNA | unclassified],
+        sizes int64[3] on the host).  detect.py:680,601-663."""
+        h = self._need()
+        n = rec.shape[0]
+        labels = torch.as_tensor(labels, dtype=torch.int8).to(self._device).contiguous()
+        if labels.numel() != n:
+            raise ValueError("labels/records mismatch")
+        with torch.cuda.device(self._device):
+            out = torch.empty(d_text.numel() + 1, dtype=torch.uint8, device=self._device)
+            sizes = torch.zeros(3, dtype=torch.int64, device=self._device)
+            rc = self._lib.rd_partition_records_device(h, _ptr(d_text) if n else None, _ptr(rec) if n else None, n,
+                                                       _ptr(labels) if n else None, _ptr(out), _ptr(sizes), self._stream())
+        _lib.check(self._lib, h, rc, "rd_partition_records_device")
+        sizes = sizes.cpu()
+        return out[:int(sizes.sum())], sizes
+
+    def fastq_submit(self, slot, bufs, lens, final_chunk, max_records, max_len, outs, labels=None, mode="none",
+                     semantics=None, precision=None):
+        """Streaming form: host FASTQ block(s) in (numpy uint8, one per end), host outs (numpy uint8, capacity
+        len + 1) filled by the time ``fastq_collect(slot)`` returns.  → (n_records, consumed[ends], out_bytes[ends])."""
+        h = self._need()
+        ends = len(bufs)
+        semantics = semantics or ("packed" if self.pack_seq else "padded")
+        precision = precision or self.precision
+        n = ctypes.c_int64(0)
+        consumed = (ctypes.c_int64 * 2)()
+        out_bytes = (ctypes.c_int64 * 2)()
+        b2, l2, o2 = (_ptr(bufs[1]), int(lens[1]), _ptr(outs[1])) if ends == 2 else (None, 0, None)
+        rc = self._lib.rd_fastq_submit(h, int(slot), ends, _ptr(bufs[0]), int(lens[0]), b2, l2, int(bool(final_chunk)),
+                                       int(max_records), int(max_len), _lib.SEM[semantics], _lib.PREC[precision],
+                                       _lib.PAIR[mode], _ptr(outs[0]), o2, _ptr(labels), ctypes.byref(n),
+                                       ctypes.cast(consumed, ctypes.c_void_p), ctypes.cast(out_bytes, ctypes.c_void_p))
+        if rc == _lib.RD_ERR_PARSE:
+            raise ValueError(self._lib.rd_last_error(h).decode("utf-8", "replace"))
+        _lib.check(self._lib, h, rc, "rd_fastq_submit")
+        return int(n.value), [int(consumed[e]) for e in range(ends)], [int(out_bytes[e]) for e in range(ends)]
+
+    def fastq_collect(self, slot):
+        """→ (sizes int64[2, 3]: text bytes per label {non-rRNA, rRNA, unclassified} in out1 / out2, counts int64[3])."""
+        sizes = (ctypes.c_int64 * 6)()
+        counts = (ctypes.c_int64 * 3)()
+        rc = self._lib.rd_fastq_collect(self._need(), int(slot), ctypes.cast(sizes, ctypes.c_void_p),
+                                        ctypes.cast(counts, ctypes.c_void_p))
+        if rc:
+            raise _lib.RdError("rd_fastq_collect failed (code %d)" % rc)
+        return np.array(list(sizes), np.int64).reshape(2, 3), np.array(list(counts), np.int64)
+
     # ---- drop-in __call__: the tensors the reference's collate functions produce -----------------
     _ALPHABET = None
 

@@ -40,7 +40,8 @@ def main():
     for rep in range(2):
         t0 = time.perf_counter()
         argv = ["-l", str(L), "-i", inp, "-o", os.path.join(d, "non.fq"), "-r", os.path.join(d, "rrna.fq"),
-                "-t", str(min(16, os.cpu_count() or 1))] + (["-d", os.environ["RD_CLI_DEVICES"]] if os.environ.get("RD_CLI_DEVICES") else [])
+                "-t", str(min(16, os.cpu_count() or 1))] + (["-d", os.environ["RD_CLI_DEVICES"]] if os.environ.get("RD_CLI_DEVICES") else []) \
+            + os.environ.get("RD_CLI_EXTRA", "").split()
         args = detect.build_parser(True).parse_args(argv)
         pred = detect.Predictor(detect.ConfigParser.from_json(os.path.join(detect.cd, "config.json")), args)
         pred.load_model()
