@@ -352,13 +352,6 @@ static int classify_host_impl(rd_handle* h, int ends,
     for (int e = 0; e < ends; ++e)
         if (!off[e] || !seq[e]) return fail(h, RD_ERR_INVALID, "rd_classify_host: NULL input buffer");
     if (!labels) return fail(h, RD_ERR_INVALID, "rd_classify_host: labels is required");
-    // reference behaviour: a zero-length read cannot be packed (torch pack_sequence raises)
-    if (semantics == RD_SEM_PACKED)
-        for (int e = 0; e < ends; ++e)
-            for (int64_t i = 0; i < n; ++i)
-                if (off[e][i + 1] <= off[e][i])
-                    return fail(h, RD_ERR_EMPTY_READ, "zero-length read at index " + std::to_string(i) +
-                                                          " cannot be classified under packed semantics");
     RD_CUDA(h, cudaSetDevice(h->device));
 
     const int64_t chunk = std::min<int64_t>(CHUNK_READS, n);
@@ -380,6 +373,21 @@ static int classify_host_impl(rd_handle* h, int ends,
     for (int64_t c = 0; c < nchunks; ++c) {
         const int st = (int)(c % rd_handle::NSTAGE);
         const int64_t s = cut[(size_t)c], t = cut[(size_t)c + 1], m = t - s;
+        // reference behaviour: a zero-length read cannot be packed (torch pack_sequence raises).  Checked chunk by
+        // chunk so that the scan of chunk c runs while the GPU works on chunk c-1.
+        if (semantics == RD_SEM_PACKED)
+            for (int e = 0; e < ends; ++e) {
+                const int64_t* o = off[e];
+                int bad = 0;
+                for (int64_t i = s; i < t; ++i) bad |= (o[i + 1] <= o[i]);       // branch-free: vectorises
+                if (bad) {
+                    int64_t i = s;
+                    while (o[i + 1] > o[i]) ++i;
+                    cudaDeviceSynchronize();
+                    return fail(h, RD_ERR_EMPTY_READ, "zero-length read at index " + std::to_string(i) +
+                                                          " cannot be classified under packed semantics");
+                }
+            }
         // stage buffers are free once the D2H of chunk c-NSTAGE has been issued and finished
         if (c >= rd_handle::NSTAGE) RD_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_out[st], 0));
         for (int e = 0; e < ends; ++e) {

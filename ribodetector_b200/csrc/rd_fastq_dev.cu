@@ -31,9 +31,22 @@ __device__ __forceinline__ bool py_space(uint32_t c) {        // what str.rstrip
 }
 
 // ---- K0a: newline positions, in order, in one pass -------------------------------------------------------
+// line_end[i] = position of the i-th '\n', with two hints for record_kernel in the top bits (the bytes next to
+// a newline are in L1 when it is found, so record_kernel need not touch the text again in the common case):
+constexpr unsigned long long LE_SPACE = 1ull << 63;     // the byte before the newline is <= 0x20: the line may need rstrip()
+constexpr unsigned long long LE_AT = 1ull << 62;        // the byte after the newline is '@'
+constexpr unsigned long long LE_POS = LE_AT - 1;
+
+// 4-bit mask of the bytes of w equal to '\n' (exact SWAR zero-byte test, then the four 0x80 flags gathered by a multiply)
+__device__ __forceinline__ uint32_t nl_nibble(uint32_t w) {
+    const uint32_t x = w ^ 0x0A0A0A0Au;
+    const uint32_t t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);       // 0x80 in every zero byte of x
+    return ((t >> 7) * 0x01020408u) >> 24;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 nl_index_kernel(const uint8_t* __restrict__ buf, int64_t len, int64_t ntiles, unsigned long long* desc, int* ticket,
-                int64_t* __restrict__ line_end, int64_t cap, int64_t* __restrict__ info) {
+                unsigned long long* __restrict__ line_end, int64_t cap, int64_t* __restrict__ info) {
     __shared__ int64_t s_tile, s_base;
     __shared__ int s_warp[SCAN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -41,8 +54,7 @@ nl_index_kernel(const uint8_t* __restrict__ buf, int64_t len, int64_t ntiles, un
     __syncthreads();
     const int64_t tile = s_tile;
     const int64_t p0 = tile * SCAN_TILE + (int64_t)tid * 64;
-    uint32_t m[16];                                            // 0x01 in every byte that is '\n'
-    int cnt = 0;
+    uint32_t mlo = 0u, mhi = 0u;                               // bit b of (mhi:mlo): byte p0 + b is '\n'
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int64_t pos = p0 + 16 * j;
@@ -55,12 +67,10 @@ nl_index_kernel(const uint8_t* __restrict__ buf, int64_t len, int64_t ntiles, un
                 if (pos + b < len) w[b >> 2] |= (uint32_t)buf[pos + b] << (8 * (b & 3));
             v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        m[4 * j + 0] = __vcmpeq4(v.x, 0x0A0A0A0Au) & 0x01010101u;
-        m[4 * j + 1] = __vcmpeq4(v.y, 0x0A0A0A0Au) & 0x01010101u;
-        m[4 * j + 2] = __vcmpeq4(v.z, 0x0A0A0A0Au) & 0x01010101u;
-        m[4 * j + 3] = __vcmpeq4(v.w, 0x0A0A0A0Au) & 0x01010101u;
-        cnt += __popc(m[4 * j + 0]) + __popc(m[4 * j + 1]) + __popc(m[4 * j + 2]) + __popc(m[4 * j + 3]);
+        const uint32_t m16 = nl_nibble(v.x) | (nl_nibble(v.y) << 4) | (nl_nibble(v.z) << 8) | (nl_nibble(v.w) << 12);
+        if (j < 2) mlo |= m16 << (16 * j); else mhi |= m16 << (16 * (j - 2));
     }
+    const int cnt = __popc(mlo) + __popc(mhi);
     // exclusive rank of this thread's first newline inside the tile
     int incl = cnt;
 #pragma unroll
@@ -109,13 +119,18 @@ nl_index_kernel(const uint8_t* __restrict__ buf, int64_t len, int64_t ntiles, un
     __syncthreads();
     int64_t rank = s_base + wbase + (incl - cnt);
 #pragma unroll
-    for (int w = 0; w < 16; ++w) {
-        uint32_t mm = m[w];
+    for (int half = 0; half < 2; ++half) {
+        uint32_t mm = half ? mhi : mlo;
         while (mm) {
-            const int bit = __ffs(mm) - 1;
-            if (rank < cap) line_end[rank] = p0 + 4 * w + (bit >> 3);
-            ++rank;
+            const int64_t pos = p0 + 32 * half + (__ffs(mm) - 1);
             mm &= mm - 1;
+            if (rank < cap) {
+                unsigned long long v = (unsigned long long)pos;
+                if (pos == 0 || buf[pos - 1] <= 0x20) v |= LE_SPACE;             // (L1 hits: this CTA just loaded the lines)
+                if (pos + 1 < len && buf[pos + 1] == '@') v |= LE_AT;
+                line_end[rank] = v;
+            }
+            ++rank;
         }
     }
 }
@@ -123,7 +138,7 @@ nl_index_kernel(const uint8_t* __restrict__ buf, int64_t len, int64_t ntiles, un
 // ---- K0b: records.  info: [0] newlines (in), [1] records n, [2] consumed bytes, [4] first bad record * 4 + kind
 __global__ void __launch_bounds__(256)
 record_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, int64_t max_records,
-              const int64_t* __restrict__ line_end, int64_t* __restrict__ rec, int64_t* __restrict__ info) {
+              const unsigned long long* __restrict__ line_end, int64_t* __restrict__ rec, int64_t* __restrict__ info) {
     const int64_t n_nl = info[0];
     const bool open_tail = final_chunk && len > 0 && buf[len - 1] != '\n';      // last line without a newline
     const int64_t n_lines = n_nl + (open_tail ? 1 : 0);
@@ -132,22 +147,28 @@ record_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, int
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r == 0) {
         info[1] = n;
-        info[2] = n == 0 ? 0 : (4 * n - 1 < n_nl ? line_end[4 * n - 1] + 1 : len);
+        info[2] = n == 0 ? 0 : (4 * n - 1 < n_nl ? (int64_t)(line_end[4 * n - 1] & LE_POS) + 1 : len);
     }
     if (r >= n) return;
+    // the five newlines around this record: the one closing the previous record, then its own four
+    unsigned long long le[5];
+    le[0] = r == 0 ? 0ull : line_end[4 * r - 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) le[k + 1] = 4 * r + k < n_nl ? line_end[4 * r + k] : ((unsigned long long)len | LE_SPACE);
     int64_t v[8];
     int kind = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int64_t li = 4 * r + k;
-        const int64_t b = li == 0 ? 0 : line_end[li - 1] + 1;
-        int64_t x = li < n_nl ? line_end[li] : len;
-        while (x > b && py_space(buf[x - 1])) --x;                               // line.rstrip()
+        const int64_t b = (r == 0 && k == 0) ? 0 : (int64_t)(le[k] & LE_POS) + 1;
+        int64_t x = (int64_t)(le[k + 1] & LE_POS);
+        if (le[k + 1] & LE_SPACE)
+            while (x > b && py_space(buf[x - 1])) --x;                           // line.rstrip()
         if (x == b && kind == 0) kind = 1;                                       // blank line: the reference raises IndexError
         v[2 * k] = b;
         v[2 * k + 1] = x;
     }
-    if (kind == 0 && buf[v[0]] != '@') kind = 2;
+    const bool at = r == 0 ? buf[0] == '@' : (le[0] & LE_AT) != 0ull;
+    if (kind == 0 && !at) kind = 2;
     if (kind) atomicMin(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)(r * 4 + kind));
     longlong2* o = reinterpret_cast<longlong2*>(rec + 8 * r);
     o[0] = make_longlong2(v[0], v[1]);
@@ -262,13 +283,36 @@ part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ re
         const int t0 = (int)(a.y - a.x) + 1, t1 = t0 + (int)(b.y - b.x) + 1, t2 = t1 + (int)(c.y - c.x) + 1,
                   t3 = t2 + (int)(d.y - d.x) + 1;
         uint8_t* o = out + s_dst[slot];
-        for (int j = lane; j < t3; j += 32) {        // output byte j: which line it belongs to, or the '\n' closing one
-            int64_t src; int end;
-            if (j < t0) { src = a.x + j; end = t0; }
-            else if (j < t1) { src = b.x + (j - t0); end = t1; }
-            else if (j < t2) { src = c.x + (j - t1); end = t2; }
-            else { src = d.x + (j - t2); end = t3; }
-            o[j] = j == end - 1 ? (uint8_t)'\n' : buf[src];
+        if (a.y + 1 == b.x && b.y + 1 == c.x && c.y + 1 == d.x) {
+            // nothing was stripped: the record text is one contiguous range of the input plus the closing '\n'.
+            // Copy it as 4-byte words aligned on the OUTPUT; the input words are realigned with a funnel shift.
+            const uint8_t* src = buf + a.x;
+            const int nbytes = t3 - 1;
+            int head = (int)((4u - (uint32_t)(uintptr_t)o) & 3u);
+            if (head > nbytes) head = nbytes;
+            if (lane < head) o[lane] = src[lane];
+            const int nw = (nbytes - head) >> 2;
+            const uint8_t* s2 = src + head;
+            const uint32_t sh = (uint32_t)(uintptr_t)s2 & 3u;
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - sh);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(o + head);
+            for (int w = lane; w < nw; w += 32) {
+                const uint32_t lo = sw[w];
+                const uint32_t hi = sh ? sw[w + 1] : 0u;      // (the aligned word holding the range's last bytes)
+                ow[w] = __funnelshift_r(lo, hi, 8u * sh);
+            }
+            const int done = head + 4 * nw;
+            if (lane < nbytes - done) o[done + lane] = src[done + lane];
+            if (lane == 0) o[nbytes] = (uint8_t)'\n';
+        } else {
+            for (int j = lane; j < t3; j += 32) {    // output byte j: which line it belongs to, or the '\n' closing one
+                int64_t src; int end;
+                if (j < t0) { src = a.x + j; end = t0; }
+                else if (j < t1) { src = b.x + (j - t0); end = t1; }
+                else if (j < t2) { src = c.x + (j - t1); end = t2; }
+                else { src = d.x + (j - t2); end = t3; }
+                o[j] = j == end - 1 ? (uint8_t)'\n' : buf[src];
+            }
         }
     }
 }
@@ -281,7 +325,7 @@ struct rd_fq_state {
     // scan scratch (used on s_in only, in order)
     unsigned long long* d_desc = nullptr; int64_t cap_desc = 0;
     int* d_ticket = nullptr;
-    int64_t* d_line_end[2] = {nullptr, nullptr}; int64_t cap_lines[2] = {0, 0};
+    unsigned long long* d_line_end[2] = {nullptr, nullptr}; int64_t cap_lines[2] = {0, 0};
     // partition scratch (s_cmp only)
     int64_t* d_blocksum = nullptr; int64_t cap_blk = 0;
     // streaming slots
@@ -487,7 +531,7 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
                 if (n == 0) { consumed2[e] = 0; continue; }
                 RD_CUDA(h, cudaMemcpyAsync(s->h_info + 16, s->d_line_end[e] + (4 * n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->s_in));
                 RD_CUDA(h, cudaStreamSynchronize(h->s_in));
-                consumed2[e] = s->h_info[16] + 1;
+                consumed2[e] = (int64_t)((unsigned long long)s->h_info[16] & ((1ull << 62) - 1)) + 1;
             }
     *n_records = n;
     if (n == 0) return RD_OK;

@@ -63,6 +63,7 @@ class FastqGpuStream:
         self.num_seqs = 0
         self.counts = np.zeros(3, np.int64)
         self.stage_seconds = {"read": 0.0, "submit": 0.0, "collect": 0.0, "write": 0.0}
+        self.setup_seconds = 0.0                 # page-locking the block buffers (once per unit)
 
     # ---- reading -------------------------------------------------------------------------------------
     def _fill(self, e, buf, start):
@@ -110,6 +111,7 @@ class FastqGpuStream:
         self.file_pos = [0] * ends
         self.eof = [False] * ends
         self.pool = ThreadPoolExecutor(self.threads)
+        self.wpool = ThreadPoolExecutor(2)
         units = [_Unit(d, s, ends, self.block_bytes) for s in range(2) for d in range(len(self.models))]
         free_units = queue.Queue()
         for u in units:
@@ -129,7 +131,7 @@ class FastqGpuStream:
                     sizes, counts = self.models[u.dev].fastq_collect(u.slot)
                     t1 = time.perf_counter()
                     busy["collect"] += t1 - t0
-                    for e in range(ends):
+                    def put(e):
                         s0, s1, s2 = (int(x) for x in sizes[e])
                         mv = memoryview(u.out[e])
                         if s0:
@@ -138,6 +140,11 @@ class FastqGpuStream:
                             sinks["rrna"][e].write(mv[s0:s0 + s1])
                         if s2 and sinks.get("unc"):
                             sinks["unc"][e].write(mv[s0 + s1:s0 + s1 + s2])
+
+                    if ends == 2:                # the two ends go to different files: write them side by side
+                        list(self.wpool.map(put, range(2)))
+                    else:
+                        put(0)
                     busy["write"] += time.perf_counter() - t1
                     self.counts += counts
                     self.num_seqs += n
@@ -154,7 +161,9 @@ class FastqGpuStream:
                 u = free_units.get()
                 if u is None:
                     break
+                t0 = time.perf_counter()
                 u.ensure()
+                self.setup_seconds += time.perf_counter() - t0
                 t0 = time.perf_counter()
                 fills = []
                 for e in range(ends):
@@ -194,6 +203,7 @@ class FastqGpuStream:
             for fh in self.fh:
                 fh.close()
             self.pool.shutdown()
+            self.wpool.shutdown()
         if errors:
             raise errors[0]
         return self.counts

@@ -200,7 +200,8 @@ class Predictor:
                 for fh in fh_non + (fh_rrna or []) + (fh_unc or []):
                     fh.close()
             self.stage_seconds = stream.stage_seconds
-            self.logger.debug('stage busy seconds: %s', stream.stage_seconds)
+            self.logger.debug('stage busy seconds: %s (page-locking buffers: %.2f s)', stream.stage_seconds, stream.setup_seconds)
+            self.setup_seconds = stream.setup_seconds
             self._report(stream.num_seqs, total, want_unc)
             return
 

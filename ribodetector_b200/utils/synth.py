@@ -34,3 +34,21 @@ def synth_reads(n, min_len, max_len, seed, n_frac=0.001):
 def to_strings(seq, off):
     b = seq.tobytes()
     return [b[off[i]:off[i + 1]].decode("latin-1") for i in range(len(off) - 1)]
+
+
+def fastq_text(n, length, seed, n_frac=0.001):
+    """FASTQ text of n fixed-length reads: "@r%09d" / seq / "+" / 'I' x length, '\n' line ends → uint8 array."""
+    seq, _ = synth_reads_fixed(n, length, seed, n_frac)
+    w = 2 + 9 + 1 + length + 1 + 2 + length + 1
+    rec = np.empty((n, w), np.uint8)
+    rec[:, 0], rec[:, 1] = ord("@"), ord("r")
+    idx = np.arange(n)
+    for d in range(9):
+        rec[:, 2 + 8 - d] = ord("0") + (idx // 10 ** d) % 10
+    rec[:, 11] = ord("\n")
+    rec[:, 12:12 + length] = seq.reshape(n, length)
+    rec[:, 12 + length] = ord("\n")
+    rec[:, 13 + length], rec[:, 14 + length] = ord("+"), ord("\n")
+    rec[:, 15 + length:15 + 2 * length] = ord("I")
+    rec[:, 15 + 2 * length] = ord("\n")
+    return rec.reshape(-1)
