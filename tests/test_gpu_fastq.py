@@ -224,3 +224,26 @@ def test_cli_default_is_device_ingest_and_equals_host_ingest(gpu_model, tmp_path
     assert (tmp_path / "a.fq").read_bytes() == (tmp_path / "b.fq").read_bytes()
     assert gzip.open(tmp_path / "ar.fq.gz").read() == gzip.open(tmp_path / "br.fq.gz").read()
     assert (a.num_seqs, a.num_rrna) == (b.num_seqs, b.num_rrna) == (8000, b.num_rrna)
+
+
+def test_streaming_round_robin_over_two_handles(gpu_model, weights, tmp_path):
+    """Blocks alternate between handles (as they do between GPUs): 4 units in flight, output still in file order."""
+    from ribodetector_b200.data_loader.fastq_gpu import FastqGpuStream
+    from ribodetector_b200.model import SeqModel
+    second = SeqModel(4, 128, 1, 2, pack_seq=True)
+    second.load_state_dict(weights)
+    second.to("cuda:0").eval()
+    try:
+        f1, f2 = _write_pairs(tmp_path, 12000)
+        outs = {}
+        for tag, models in (("one", [gpu_model]), ("two", [gpu_model, second])):
+            names = [tmp_path / ("%s_%d.fq" % (tag, i)) for i in range(4)]
+            fhs = [open(x, "wb") for x in names]
+            st = FastqGpuStream(models, [str(f1), str(f2)], 100, mode="rrna", block_bytes=1 << 17, threads=2)
+            counts = st.run({"non": fhs[0:2], "rrna": fhs[2:4], "unc": None})
+            for fh in fhs:
+                fh.close()
+            outs[tag] = ([x.read_bytes() for x in names], counts.tolist(), st.num_seqs)
+        assert outs["one"] == outs["two"] and outs["one"][2] == 12000
+    finally:
+        second.close()
