@@ -488,3 +488,21 @@ def test_cli_fasta_input_is_uppercased_joined_and_classified(gpu_model, numpy_or
     want = _expected_files(recs, lab)
     assert out.read_text() == want[0] and rr.read_text() == want[1]
     assert pred.num_seqs == n and pred.num_rrna == int((lab == 1).sum())
+
+
+def test_full_size_config1_50m_reads_periodic(gpu_model):
+    """BASELINE configs[1] at its full size through ONE host-API call: 12 x 2^22 = 50 331 648 reads of 100 bp, 5.03 GB
+    of bases (offsets beyond 2^32, 25 pipeline chunks).  The batch is one 2^22-read period repeated, so the labels
+    must repeat bit for bit, equal the device path's labels of one period, and the counts must be 12 x its histogram."""
+    period, reps = 1 << 22, 12
+    seq1, _ = synth.synth_reads_fixed(period, 100, synth.SEED_BASE + 2)
+    seq = np.tile(seq1, reps)
+    off = np.arange(period * reps + 1, dtype=np.int64) * 100
+    assert int(off[-1]) > 1 << 32
+    r = gpu_model.classify_host(seq, off, 100, want_logits=False)
+    labels = r["labels"].numpy().reshape(reps, period)
+    one = gpu_model.classify(seq1, off[:period + 1], 100)[2].cpu().numpy()
+    assert np.array_equal(labels[0], one)
+    assert (labels == labels[0][None, :]).all()
+    assert np.array_equal(r["counts"].numpy(), reps * pairs.counts(one))
+    assert int(r["counts"].sum()) == period * reps
