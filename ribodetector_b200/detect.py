@@ -1,17 +1,25 @@
 """``ribodetector`` — the reference's command line (``ribodetector/detect.py:763-809``) on the B200
 hot path.  Same flags, same ``config.json`` model description, same output files and final count
 lines; the batch loops of ``Predictor.run`` / ``run_with_chunks`` (``detect.py:121-523``) are one
-streaming pipeline here:
+streaming pipeline here.
 
-    reader thread(s): file block → rd_scan_fastx (record index + sequence bytes)
+FASTQ inputs (plain or gz; the default path, ``data_loader/fastq_gpu.py``): the host only moves bytes —
+
+    producer thread : file block → page-locked buffer → rd_fastq_submit (H2D, K0 record scan; returns when the
+                      record count and the cut position are known; K1-K3 classify and K4 label partition stay queued)
+    consumer thread : rd_fastq_collect → one write() per label group and output file, input order kept
+    2 x n_devices blocks of up to 256 MB are in flight, round-robin over the visible GPUs
+
+FASTA inputs, ``--chunk_size`` runs and ``--host_ingest``:
+
+    reader thread(s): file block → rd_scan_fastx (record index + sequence bytes, host C++)
     main thread     : rd_classify_host / rd_classify_pairs_host on every visible GPU (reads sharded
                       contiguously across devices, one handle per device)
     writer thread   : rd_partition_records → non-rRNA / rRNA / unclassified files, input order kept
 
-Memory is bounded by the chunk size (``--chunk_size`` keeps its meaning: chunk = batch_size x
-chunk_size reads, ``detect.py:370-371``; without it chunks of 1 Mi reads are used), so there is no
-whole-file mode to run out of RAM.  ``-m`` only feeds the reference's batch-size formula that the
-log line reports; ``-t`` sizes the host-side partition threads.
+Memory is bounded by the block / chunk size (``--chunk_size`` keeps its meaning: chunk = batch_size x
+chunk_size reads, ``detect.py:370-371``), so there is no whole-file mode to run out of RAM.  ``-m`` only
+feeds the reference's batch-size formula that the log line reports; ``-t`` sizes the host-side threads.
 """
 import argparse
 import math
