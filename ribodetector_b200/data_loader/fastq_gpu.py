@@ -112,6 +112,7 @@ class FastqGpuStream:
         self.eof = [False] * ends
         self.pool = ThreadPoolExecutor(self.threads)
         self.wpool = ThreadPoolExecutor(2)
+        self.rpool = ThreadPoolExecutor(2)
         units = [_Unit(d, s, ends, self.block_bytes) for s in range(2) for d in range(len(self.models))]
         free_units = queue.Queue()
         for u in units:
@@ -165,11 +166,13 @@ class FastqGpuStream:
                 u.ensure()
                 self.setup_seconds += time.perf_counter() - t0
                 t0 = time.perf_counter()
-                fills = []
-                for e in range(ends):
+                def fill(e):
                     k = tails[e].size
                     u.inp[e][:k] = tails[e]
-                    fills.append(self._fill(e, u.inp[e], k))
+                    return self._fill(e, u.inp[e], k)
+
+                # (two ends: both files are read / inflated side by side — zlib releases the GIL)
+                fills = list(self.rpool.map(fill, range(ends))) if ends == 2 else [fill(0)]
                 final = all(self.eof)
                 t1 = time.perf_counter()
                 busy["read"] += t1 - t0
@@ -204,6 +207,7 @@ class FastqGpuStream:
                 fh.close()
             self.pool.shutdown()
             self.wpool.shutdown()
+            self.rpool.shutdown()
         if errors:
             raise errors[0]
         return self.counts

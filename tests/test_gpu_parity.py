@@ -506,3 +506,39 @@ def test_full_size_config1_50m_reads_periodic(gpu_model):
     assert (labels == labels[0][None, :]).all()
     assert np.array_equal(r["counts"].numpy(), reps * pairs.counts(one))
     assert int(r["counts"].sum()) == period * reps
+
+
+def _tile_reads(seq1, off1, reps):
+    """`reps` copies of a batch, concatenated → (seq, off) with offsets continuing across the copies."""
+    n1, b1 = len(off1) - 1, int(off1[-1])
+    seq = np.tile(seq1, reps)
+    off = (off1[None, :-1] + (np.arange(reps, dtype=np.int64) * b1)[:, None]).reshape(-1)
+    return seq, np.concatenate([off, [b1 * reps]]).astype(np.int64), n1
+
+
+def test_full_size_config5_50m_mixed_length_reads_periodic(gpu_model):
+    """BASELINE configs[4] at its full size: 24 x 2^21 = 50 331 648 reads of 40-300 bp (8.6 GB of bases), -l 300,
+    one host-API call; labels repeat bit for bit with the period and equal the device path's."""
+    seq1, off1 = synth.synth_reads(1 << 21, 40, 300, synth.SEED_BASE + 5)
+    seq, off, period = _tile_reads(seq1, off1, 24)
+    r = gpu_model.classify_host(seq, off, 300, want_logits=False)
+    labels = r["labels"].numpy().reshape(24, period)
+    one = gpu_model.classify(seq1, off1, 300)[2].cpu().numpy()
+    assert np.array_equal(labels[0], one) and (labels == labels[0][None, :]).all()
+    assert np.array_equal(r["counts"].numpy(), 24 * pairs.counts(one))
+
+
+def test_full_size_config3_pairs_per_gpu_periodic(gpu_model):
+    """BASELINE configs[2] per-GPU shard at its full size: 12 x 2^20 = 12 582 912 pairs of 100 bp, -e rrna, one
+    host-API call; pair labels repeat with the period and equal pair_combine of the device path's logits."""
+    s1, o1 = synth.synth_reads_fixed(1 << 20, 100, synth.SEED_BASE + 31)
+    s2, o2 = synth.synth_reads_fixed(1 << 20, 100, synth.SEED_BASE + 32)
+    a, oa, period = _tile_reads(s1, o1, 12)
+    b, ob, _ = _tile_reads(s2, o2, 12)
+    r = gpu_model.classify_pairs_host(a, oa, b, ob, 100, mode="rrna")
+    labels = r["labels"].numpy().reshape(12, period)
+    l1, l2 = gpu_model.classify(s1, o1, 100)[0], gpu_model.classify(s2, o2, 100)[0]
+    one = gpu_model.pair_combine(l1, l2, "rrna").cpu().numpy()
+    assert np.array_equal(labels[0], one) and (labels == labels[0][None, :]).all()
+    assert np.array_equal(r["counts"].numpy(), 12 * pairs.counts(one))
+    assert int(r["counts"].sum()) == 12 * period
