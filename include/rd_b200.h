@@ -181,6 +181,13 @@ int rd_partition_records(const uint8_t* buf, int format, int64_t n, const int64_
 
 const char* rd_fastx_last_error(void);
 
+/* Replaces `gzip.open` (seq_encoder.py:43-53) for BGZF-framed .gz text (bgzip, bcl2fastq / BCL Convert output): every
+ * member carries its compressed size, so the complete members of in[0..in_len) are located without inflating and
+ * inflated on `threads` host threads into out (CRC-32 checked), as many as fit in out_cap.  Returns the bytes written
+ * (0: no complete member fits yet), *in_used = input bytes consumed; -RD_ERR_UNSUPPORTED if in does not start with a
+ * BGZF member (use a serial gzip reader), -RD_ERR_PARSE on a corrupt member. */
+int64_t rd_bgzf_inflate(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap, int64_t* in_used, int threads);
+
 /* ---- the same edges on the device, for uncompressed FASTQ text resident in HBM --------------------------
  * K0.  Replaces seq_parser's FASTQ branch (fastx_parser.py:15-47) with rd_scan_fastx's semantics: d_buf[0..len)
  * (16-byte aligned) is scanned in one pass; d_rec receives int64[8] per record = [begin, end) of the header,

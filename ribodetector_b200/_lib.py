@@ -39,6 +39,7 @@ SIGNATURES = {
     "rd_scan_fastx": (_i64, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i]),
     "rd_partition_records": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rd_fastx_last_error": (_c.c_char_p, []),
+    "rd_bgzf_inflate": (_i64, [_vp, _i64, _vp, _i64, _vp, _i]),
     "rd_scan_fastq_device": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp, _vp]),
     "rd_classify_records": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rd_partition_records_device": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -265,3 +265,88 @@ extern "C" int rd_partition_records(const uint8_t* buf, int format, int64_t n, c
     if (out_non || out_rrna || out_unc) run(true);
     return RD_OK;
 }
+
+// ---- parallel inflate of BGZF text (bgzip, bcl2fastq / BCL Convert FASTQ.gz): every gzip member carries its own
+// compressed size in a 'BC' extra subfield, so member boundaries are known without inflating and the members
+// (<= 64 KB of text each) can be inflated side by side.  The reference reads .gz through Python's gzip module on
+// one thread (seq_encoder.py:43-53 `gzip.open`), which is what bounds it on compressed inputs.
+#include <zlib.h>
+
+namespace {
+struct BgzfMember { int64_t in_off; int32_t in_len, hdr_len; int64_t out_off; uint32_t isize; };
+
+// -> total member size, or 0 if [p, p+avail) does not start with a complete BGZF member header, or -1 if it is not BGZF
+inline int64_t bgzf_member_size(const uint8_t* p, int64_t avail, int32_t* hdr_len) {
+    if (avail < 18) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return -1;
+    const int xlen = p[10] | (p[11] << 8);
+    if (avail < 12 + xlen) return 0;
+    int64_t bsize = -1;
+    for (int i = 12; i + 4 <= 12 + xlen;) {
+        const int slen = p[i + 2] | (p[i + 3] << 8);
+        if (p[i] == 'B' && p[i + 1] == 'C' && slen == 2 && i + 6 <= 12 + xlen) bsize = (p[i + 4] | (p[i + 5] << 8)) + 1;
+        i += 4 + slen;
+    }
+    if (bsize < 0 || (p[3] & ~4)) return -1;          // no BC subfield, or name/comment/hcrc fields we do not expect in BGZF
+    *hdr_len = 12 + xlen;
+    return bsize;
+}
+}  // namespace
+
+extern "C" int64_t rd_bgzf_inflate(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap, int64_t* in_used,
+                                   int threads) {
+    g_fx_err.clear();
+    if (!in || in_len < 0 || !out || out_cap < 0 || !in_used) { g_fx_err = "rd_bgzf_inflate: bad arguments"; return -RD_ERR_INVALID; }
+    *in_used = 0;
+    std::vector<BgzfMember> mem;
+    int64_t ip = 0, op = 0;
+    while (ip < in_len) {
+        int32_t hl = 0;
+        const int64_t sz = bgzf_member_size(in + ip, in_len - ip, &hl);
+        if (sz < 0) {
+            if (mem.empty()) { g_fx_err = "not a BGZF stream (gzip member without a 'BC' size field)"; return -RD_ERR_UNSUPPORTED; }
+            break;                                       // (the caller sees in_used < in_len and an unreadable next member)
+        }
+        if (sz == 0 || ip + sz > in_len || sz < hl + 8) break;       // incomplete member: wait for more input
+        const uint8_t* t = in + ip + sz - 4;
+        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (op + (int64_t)isize > out_cap) break;                   // output full
+        mem.push_back({ip, (int32_t)sz, hl, op, isize});
+        ip += sz;
+        op += isize;
+    }
+    if (mem.empty()) return 0;
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if ((int64_t)mem.size() < 4 * threads) threads = 1;
+    std::vector<int> bad((size_t)threads, 0);
+    auto work = [&](int t) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { bad[(size_t)t] = 1; return; }
+        const size_t lo = mem.size() * (size_t)t / (size_t)threads, hi = mem.size() * (size_t)(t + 1) / (size_t)threads;
+        for (size_t i = lo; i < hi; ++i) {
+            const BgzfMember& m = mem[i];
+            zs.next_in = const_cast<Bytef*>(in + m.in_off + m.hdr_len);
+            zs.avail_in = (uInt)(m.in_len - m.hdr_len - 8);
+            zs.next_out = out + m.out_off;
+            zs.avail_out = m.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            const uint8_t* c = in + m.in_off + m.in_len - 8;
+            const uint32_t want = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(0L, out + m.out_off, m.isize) != want) { bad[(size_t)t] = 1; break; }
+            inflateReset(&zs);
+        }
+        inflateEnd(&zs);
+    };
+    if (threads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto& th : pool) th.join();
+    }
+    for (int t = 0; t < threads; ++t)
+        if (bad[(size_t)t]) { g_fx_err = "BGZF: corrupt member (inflate or CRC-32 failed)"; return -RD_ERR_PARSE; }
+    *in_used = ip;
+    return op;
+}

@@ -8,7 +8,6 @@ GPU, indexed (K0), classified (K1-K3), partitioned by label (K4) and copied back
 byte ranges that go to the output files with one ``write`` each.  A producer thread (read + submit) and
 a consumer thread (collect + write) keep ``2 x n_devices`` blocks in flight, in file order.
 """
-import gzip
 import os
 import queue
 import threading
@@ -17,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from .fastx import _host_array, get_seq_format
+from .fastx import _host_array, get_seq_format, open_text
 
 
 class _Unit:
@@ -107,7 +106,7 @@ class FastqGpuStream:
     # ---- the pipeline ----------------------------------------------------------------------------------
     def run(self, sinks):
         ends = self.ends
-        self.fh = [open(p, "rb", buffering=0) if plain else gzip.open(p, "rb") for p, plain in zip(self.inputs, self.plain)]
+        self.fh = [open_text(p, not plain, self.threads) for p, plain in zip(self.inputs, self.plain)]
         self.file_pos = [0] * ends
         self.eof = [False] * ends
         self.pool = ThreadPoolExecutor(self.threads)

@@ -85,6 +85,96 @@ def _p(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
+class BgzfReader:
+    """File-like reader (readinto / close) of BGZF-framed .gz text — bgzip, bcl2fastq / BCL Convert FASTQ.gz: every
+    gzip member states its compressed size, so `rd_bgzf_inflate` inflates the members of a buffer side by side on
+    `threads` host threads.  The reference reads every .gz through `gzip.open` on one thread (seq_encoder.py:43-53)."""
+
+    COMP = 32 << 20
+
+    def __init__(self, path, threads=8):
+        self.fh = open(path, "rb", buffering=0)
+        self.threads = max(1, int(threads))
+        self.lib = _lib.load_library()
+        self.comp = np.empty(self.COMP, np.uint8)
+        self.lo = self.hi = 0                       # unread compressed bytes are comp[lo:hi]
+        self.raw_eof = False
+        self.spill = b""                            # text of one member that did not fit the caller's buffer
+
+    @staticmethod
+    def sniff(path):
+        """True if the file starts with a BGZF member (gzip FEXTRA with a 'BC' subfield)."""
+        with open(path, "rb") as f:
+            h = f.read(18)
+        return len(h) >= 18 and h[:4] == b"\x1f\x8b\x08\x04" and h[12:14] == b"BC"
+
+    def _refill(self):
+        if self.lo and self.lo < self.hi:
+            self.comp[:self.hi - self.lo] = self.comp[self.lo:self.hi]
+        self.hi -= self.lo
+        self.lo = 0
+        mv = memoryview(self.comp)
+        while self.hi < self.COMP and not self.raw_eof:
+            k = self.fh.readinto(mv[self.hi:])
+            if not k:
+                self.raw_eof = True
+            self.hi += k or 0
+
+    def readinto(self, b):
+        out = np.frombuffer(b, np.uint8)
+        pos = 0
+        if self.spill:
+            k = min(len(self.spill), out.size)
+            out[:k] = np.frombuffer(self.spill[:k], np.uint8)
+            self.spill = self.spill[k:]
+            pos = k
+        used = ctypes.c_int64(0)
+        while pos < out.size:
+            if self.hi - self.lo < (1 << 17) and not self.raw_eof:
+                self._refill()
+            if self.lo == self.hi:
+                break                                # end of file
+            n = self.lib.rd_bgzf_inflate(ctypes.c_void_p(self.comp.ctypes.data + self.lo), self.hi - self.lo,
+                                         ctypes.c_void_p(out.ctypes.data + pos), out.size - pos, ctypes.byref(used),
+                                         self.threads)
+            if n < 0:
+                raise ValueError("%s" % self.lib.rd_fastx_last_error().decode("utf-8", "replace"))
+            self.lo += used.value
+            pos += n
+            if used.value == 0:
+                if self.hi - self.lo < (1 << 17) and not self.raw_eof:
+                    continue                         # an incomplete member: read more
+                if self.hi - self.lo >= 18 and pos < out.size:
+                    # the next member's text does not fit what is left of `out`: inflate it aside and hand out a part
+                    import zlib
+                    d = zlib.decompressobj(31)
+                    self.spill = d.decompress(self.comp[self.lo:self.hi].tobytes())
+                    if not d.eof:
+                        raise ValueError("BGZF: truncated or corrupt member")
+                    self.lo = self.hi - len(d.unused_data)
+                    k = min(len(self.spill), out.size - pos)
+                    out[pos:pos + k] = np.frombuffer(self.spill[:k], np.uint8)
+                    self.spill = self.spill[k:]
+                    pos += k
+                    continue
+                if self.raw_eof and self.lo < self.hi:
+                    raise ValueError("BGZF: truncated last member")
+                break
+        return pos
+
+    def close(self):
+        self.fh.close()
+
+
+def open_text(path, gz, threads=8):
+    """Binary reader of a sequence file's TEXT: the file itself, a parallel BGZF reader, or Python's gzip."""
+    if not gz:
+        return open(path, "rb", buffering=0)
+    if BgzfReader.sniff(path):
+        return BgzfReader(path, threads)
+    return gzip.open(path, "rb")
+
+
 def _host_array(n, dtype, pinned):
     """numpy array, page-locked when a CUDA device is there: the sequence bytes and offsets go to the
     GPU by cudaMemcpyAsync straight from these recycled buffers."""
@@ -147,7 +237,7 @@ class FastxReader:
     def __init__(self, path, max_records=1 << 22, block_bytes=1 << 28, threads=4, pinned=False):
         fmt = get_seq_format(path)
         self.format = "fasta" if fmt.startswith("fa") else "fastq"
-        self.fh = gzip.open(path, "rb") if fmt.endswith("gz") else open(path, "rb", buffering=0)
+        self.fh = open_text(path, fmt.endswith("gz"), threads)
         self.plain = not fmt.endswith("gz")
         self.file_pos = 0
         self.pool = None

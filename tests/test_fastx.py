@@ -191,3 +191,64 @@ def test_scanner_differential_fuzz_against_reference_parser(tmp_path):
                     assert typ == "fastq" and any(not l.startswith("@") for l in text.splitlines()[0::4] if l.strip())
                     continue
                 assert got == want, (trial, kw)
+
+
+def _bgzf_bytes(text, block=0xff00, eof_marker=True):
+    """BGZF framing of `text` (what bgzip / bcl2fastq write): <= 64 KB members with a 'BC' size subfield."""
+    import struct
+    import zlib
+    out = []
+    chunks = [text[i:i + block] for i in range(0, len(text), block)] + ([b""] if eof_marker else [])
+    for c in chunks:
+        z = zlib.compressobj(6, zlib.DEFLATED, -15)
+        d = z.compress(c) + z.flush()
+        bsize = 12 + 6 + len(d) + 8 - 1
+        out.append(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize)
+                   + d + struct.pack("<II", zlib.crc32(c), len(c)))
+    return b"".join(out)
+
+
+def test_bgzf_reader_inflates_members_in_parallel(tmp_path):
+    from ribodetector_b200.data_loader import BgzfReader, open_text
+    rng = np.random.default_rng(3)
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(20, 150))).tolist()), b"I" * 10)
+                    for i in range(40000))
+    p = tmp_path / "x.fq.gz"
+    p.write_bytes(_bgzf_bytes(text))
+    assert BgzfReader.sniff(str(p)) and gzip.open(p).read() == text
+    for threads, step in ((1, 1 << 20), (4, 1 << 22), (3, 70001), (2, 1000)):     # 1000 < a member: the spill path
+        r = open_text(str(p), True, threads)
+        assert isinstance(r, BgzfReader)
+        got = bytearray()
+        buf = np.empty(step, np.uint8)
+        while True:
+            k = r.readinto(memoryview(buf))
+            if not k:
+                break
+            got += buf[:k].tobytes()
+        r.close()
+        assert bytes(got) == text, (threads, step)
+    plain_gz = tmp_path / "y.fq.gz"
+    with gzip.open(plain_gz, "wb") as f:
+        f.write(text[:1000])
+    assert not BgzfReader.sniff(str(plain_gz)) and not isinstance(open_text(str(plain_gz), True), BgzfReader)
+    # corrupt member -> error, truncated file -> error
+    raw = bytearray(_bgzf_bytes(text))
+    raw[200] ^= 0x55
+    (tmp_path / "bad.fq.gz").write_bytes(bytes(raw))
+    with pytest.raises(ValueError):
+        r = BgzfReader(str(tmp_path / "bad.fq.gz"))
+        r.readinto(memoryview(np.empty(1 << 20, np.uint8)))
+    (tmp_path / "cut.fq.gz").write_bytes(_bgzf_bytes(text)[:-500])
+    with pytest.raises(ValueError):
+        r = BgzfReader(str(tmp_path / "cut.fq.gz"))
+        buf = np.empty(1 << 24, np.uint8)
+        while r.readinto(memoryview(buf)):
+            pass
+
+
+def test_fastx_reader_takes_bgzf_input(tmp_path, golden):
+    case = golden["cases"]["fq_plain"]
+    p = tmp_path / "g.fq.gz"
+    p.write_bytes(_bgzf_bytes(case["text"].encode("latin-1"), block=37))
+    assert _read_all(str(p), block_bytes=64) == [tuple(r) for r in case["records"]]

@@ -19,12 +19,44 @@ def write_fastq(path, n, L, seed):
     return rec.size
 
 
+def write_bgzf(path, text, threads=16):
+    """BGZF framing (bgzip / bcl2fastq style: <= 64 KB members with their size in a 'BC' subfield), level 1."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    mv = memoryview(text)
+
+    def member(i):
+        c = mv[i:i + 0xff00]
+        z = zlib.compressobj(1, zlib.DEFLATED, -15)
+        d = z.compress(c) + z.flush()
+        return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 25 + len(d))
+                + d + struct.pack("<II", zlib.crc32(c), len(c)))
+
+    with open(path, "wb") as f, ThreadPoolExecutor(threads) as ex:
+        for m in ex.map(member, range(0, len(mv), 0xff00), chunksize=64):
+            f.write(m)
+        f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0\x1b\0\x03\0\0\0\0\0\0\0\0\0")
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
     L = int(sys.argv[2]) if len(sys.argv) > 2 else 100
     d = tempfile.mkdtemp(prefix="rdcli_")
     inp = os.path.join(d, "in.fq")
     size = write_fastq(inp, n, L, synth.SEED_BASE + 7)
+    gz = os.environ.get("RD_CLI_GZ", "")                  # "bgzf": BGZF-framed input, "gzip": one plain gzip member
+    if gz:
+        text = np.fromfile(inp, np.uint8)
+        os.remove(inp)
+        inp += ".gz"
+        if gz == "bgzf":
+            write_bgzf(inp, text)
+        else:
+            import gzip
+            with gzip.open(inp, "wb", compresslevel=1) as f:
+                f.write(memoryview(text))
+        print("input: %s, %.2f GB compressed" % (gz, os.path.getsize(inp) / 1e9), flush=True)
     for rep in range(2):
         for f in ("non.fq", "rrna.fq"):                 # (truncating a multi-GB output of the previous run is not the tool's time)
             if os.path.exists(os.path.join(d, f)):
