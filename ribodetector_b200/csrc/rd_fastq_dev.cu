@@ -215,45 +215,63 @@ part_sum_kernel(const int64_t* __restrict__ rec, const int8_t* __restrict__ labe
 __global__ void __launch_bounds__(1024)
 part_scan_kernel(int64_t* __restrict__ blocksum, int64_t nblk, int64_t* __restrict__ sizes3) {
     __shared__ int64_t part[1024];
-    __shared__ int64_t carry[3];
+    __shared__ int64_t total[3];
     const int tid = threadIdx.x;
-    if (tid < 3) carry[tid] = 0;
-    __syncthreads();
+    const int64_t per = (nblk + 1023) / 1024;                  // consecutive entries owned by one thread
+    const int64_t lo = tid * per, hi = lo + per < nblk ? lo + per : nblk;
     for (int c = 0; c < 3; ++c) {
-        for (int64_t base = 0; base < nblk; base += 1024) {
-            const int64_t i = base + tid;
-            const int64_t v = i < nblk ? blocksum[i * 3 + c] : 0;
-            part[tid] = v;
+        int64_t s = 0;
+        for (int64_t i = lo; i < hi; ++i) s += blocksum[i * 3 + c];
+        part[tid] = s;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {                   // inclusive Hillis-Steele scan of the per-thread sums
+            const int64_t o = tid >= d ? part[tid - d] : 0;
             __syncthreads();
-            for (int d = 1; d < 1024; d <<= 1) {
-                const int64_t o = tid >= d ? part[tid - d] : 0;
-                __syncthreads();
-                part[tid] += o;
-                __syncthreads();
-            }
-            if (i < nblk) blocksum[i * 3 + c] = carry[c] + part[tid] - v;
-            __syncthreads();
-            if (tid == 1023) carry[c] += part[1023];
+            part[tid] += o;
             __syncthreads();
         }
+        int64_t run = part[tid] - s;
+        if (tid == 1023) total[c] = part[1023];
+        __syncthreads();
+        // class c starts after the classes before it
+        run += c == 0 ? 0 : (c == 1 ? total[0] : total[0] + total[1]);
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t v = blocksum[i * 3 + c];
+            blocksum[i * 3 + c] = run;
+            run += v;
+        }
+        __syncthreads();
     }
-    if (tid == 0) { sizes3[0] = carry[0]; sizes3[1] = carry[1]; sizes3[2] = carry[2]; }
-    // class c starts after the classes before it
-    const int64_t b1 = carry[0], b2 = carry[0] + carry[1];
-    for (int64_t i = tid; i < nblk; i += 1024) { blocksum[i * 3 + 1] += b1; blocksum[i * 3 + 2] += b2; }
+    if (tid < 3) sizes3[tid] = total[tid];
 }
 
-// 256 records per CTA: in-block exclusive offsets per class, then one warp per record writes its text
+// 256 records per CTA: in-block exclusive offsets per class, then half a warp per record writes its text
 __global__ void __launch_bounds__(256)
 part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ rec, const int8_t* __restrict__ labels,
                  int64_t n, const int64_t* __restrict__ blockbase, uint8_t* __restrict__ out) {
+    __shared__ longlong2 s_rec[256][4];          // the block's slice of the record index: read from HBM once, coalesced
     __shared__ int64_t s_dst[256];
     __shared__ int s_wsum[3][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * 256;
+    {
+        const longlong2* g = reinterpret_cast<const longlong2*>(rec + 8 * r0);
+        longlong2* sflat = &s_rec[0][0];
+        const int64_t avail = (n - r0 < 256 ? n - r0 : 256) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = j * 256 + tid;
+            if (idx < avail) sflat[idx] = g[idx];
+        }
+    }
+    __syncthreads();
     const int64_t r = r0 + tid;
     int cls = 0, len = 0;
-    if (r < n) { cls = label_class(labels[r]); len = rec_text_len(rec, r); }
+    if (r < n) {
+        cls = label_class(labels[r]);
+        const longlong2 a = s_rec[tid][0], b = s_rec[tid][1], c = s_rec[tid][2], d = s_rec[tid][3];
+        len = (int)((a.y - a.x) + (b.y - b.x) + (c.y - c.x) + (d.y - d.x)) + 4;
+    }
     int incl[3], mine[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -274,12 +292,12 @@ part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ re
         s_dst[tid] = blockbase[(int64_t)blockIdx.x * 3 + cls] + before + (incl[cls] - mine[cls]);
     }
     __syncthreads();
-    for (int i = 0; i < 32; ++i) {
-        const int slot = warp * 32 + i;
-        const int64_t rr = r0 + slot;
-        if (rr >= n) break;
-        const longlong2* p = reinterpret_cast<const longlong2*>(rec + 8 * rr);
-        const longlong2 a = p[0], b = p[1], c = p[2], d = p[3];
+    const int sub = lane >> 4, hl = lane & 15;   // two records in flight per warp: twice the loads outstanding
+    for (int i = 0; i < 16; ++i) {
+        if (r0 + warp * 32 + 2 * i >= n) break;
+        const int slot = warp * 32 + 2 * i + sub;
+        if (r0 + slot >= n) continue;
+        const longlong2 a = s_rec[slot][0], b = s_rec[slot][1], c = s_rec[slot][2], d = s_rec[slot][3];
         const int t0 = (int)(a.y - a.x) + 1, t1 = t0 + (int)(b.y - b.x) + 1, t2 = t1 + (int)(c.y - c.x) + 1,
                   t3 = t2 + (int)(d.y - d.x) + 1;
         uint8_t* o = out + s_dst[slot];
@@ -290,22 +308,22 @@ part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ re
             const int nbytes = t3 - 1;
             int head = (int)((4u - (uint32_t)(uintptr_t)o) & 3u);
             if (head > nbytes) head = nbytes;
-            if (lane < head) o[lane] = src[lane];
+            if (hl < head) o[hl] = src[hl];
             const int nw = (nbytes - head) >> 2;
             const uint8_t* s2 = src + head;
             const uint32_t sh = (uint32_t)(uintptr_t)s2 & 3u;
             const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - sh);
             uint32_t* ow = reinterpret_cast<uint32_t*>(o + head);
-            for (int w = lane; w < nw; w += 32) {
+            for (int w = hl; w < nw; w += 16) {
                 const uint32_t lo = sw[w];
                 const uint32_t hi = sh ? sw[w + 1] : 0u;      // (the aligned word holding the range's last bytes)
                 ow[w] = __funnelshift_r(lo, hi, 8u * sh);
             }
             const int done = head + 4 * nw;
-            if (lane < nbytes - done) o[done + lane] = src[done + lane];
-            if (lane == 0) o[nbytes] = (uint8_t)'\n';
+            if (hl < nbytes - done) o[done + hl] = src[done + hl];
+            if (hl == 0) o[nbytes] = (uint8_t)'\n';
         } else {
-            for (int j = lane; j < t3; j += 32) {    // output byte j: which line it belongs to, or the '\n' closing one
+            for (int j = hl; j < t3; j += 16) {      // output byte j: which line it belongs to, or the '\n' closing one
                 int64_t src; int end;
                 if (j < t0) { src = a.x + j; end = t0; }
                 else if (j < t1) { src = b.x + (j - t0); end = t1; }

@@ -57,14 +57,23 @@ def main():
             with gzip.open(inp, "wb", compresslevel=1) as f:
                 f.write(memoryview(text))
         print("input: %s, %.2f GB compressed" % (gz, os.path.getsize(inp) / 1e9), flush=True)
+    paired = os.environ.get("RD_CLI_PAIRED", "")          # e.g. "rrna": a second file of mates, -e rrna (BASELINE configs[2] shape)
+    if paired:
+        inp2 = os.path.join(d, "in2.fq")
+        size += write_fastq(inp2, n, L, synth.SEED_BASE + 8)
     for rep in range(2):
-        for f in ("non.fq", "rrna.fq"):                 # (truncating a multi-GB output of the previous run is not the tool's time)
+        for f in ("non.fq", "rrna.fq", "non2.fq", "rrna2.fq"):                 # (truncating a multi-GB output of the previous run is not the tool's time)
             if os.path.exists(os.path.join(d, f)):
                 os.remove(os.path.join(d, f))
         t0 = time.perf_counter()
         argv = ["-l", str(L), "-i", inp, "-o", os.path.join(d, "non.fq"), "-r", os.path.join(d, "rrna.fq"),
                 "-t", str(min(16, os.cpu_count() or 1))] + (["-d", os.environ["RD_CLI_DEVICES"]] if os.environ.get("RD_CLI_DEVICES") else []) \
             + os.environ.get("RD_CLI_EXTRA", "").split()
+        if paired:
+            argv[argv.index("-i") + 2:argv.index("-i") + 2] = [inp2]
+            argv[argv.index("-o") + 2:argv.index("-o") + 2] = [os.path.join(d, "non2.fq")]
+            argv[argv.index("-r") + 2:argv.index("-r") + 2] = [os.path.join(d, "rrna2.fq")]
+            argv += ["-e", paired]
         args = detect.build_parser(True).parse_args(argv)
         pred = detect.Predictor(detect.ConfigParser.from_json(os.path.join(detect.cd, "config.json")), args)
         pred.load_model()
@@ -72,8 +81,9 @@ def main():
         pred.detect()
         dt = time.perf_counter() - t0
         print("       load_model %.2f s, detect %.2f s" % (t_load, dt - t_load))
-        print("run %d: %d reads, %.2f GB FASTQ in %.2f s = %.2f M reads/s (non-rRNA %d, rRNA %d)"
-              % (rep, pred.num_seqs, size / 1e9, dt, n / dt / 1e6, pred.num_nonrrna, pred.num_rrna), flush=True)
+        k = 2 if paired else 1                            # a pair counts as 2 reads
+        print("run %d: %d %s, %.2f GB FASTQ in %.2f s = %.2f M reads/s (non-rRNA %d, rRNA %d)"
+              % (rep, pred.num_seqs, "pairs" if paired else "reads", size / 1e9, dt, k * n / dt / 1e6, pred.num_nonrrna, pred.num_rrna), flush=True)
         print("       stage busy seconds:", {k: round(v, 3) for k, v in pred.stage_seconds.items()},
               "page-locking: %.2f s" % getattr(pred, "setup_seconds", 0.0), flush=True)
     for f in os.listdir(d):
