@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("RD_BENCH_PRECISION", "tc_exact"),
                     choices=["fp32", "tc_exact", "tc_fast", "tc_auto"])
     ap.add_argument("--reads-per-step", type=int, default=BATCH_READS)
-    ap.add_argument("--cpu-batches", type=int, default=12, help="1024-read batches per CPU worker in cpu_baseline")
+    ap.add_argument("--cpu-batches", type=int, default=28, help="1024-read batches per CPU worker in cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the informational tc_fast timing")
     args = ap.parse_args()
