@@ -37,9 +37,9 @@ import numpy as np  # noqa: E402
 READ_LEN = 100
 # tensor FLOPs EXECUTED per algorithmic FLOP: K = 128 + 16 input chunk, x3 passes for the fp16 split
 EXECUTED_PER_ALGORITHMIC = {"fp32": 1.0, "tc_exact": 25.0 / 8.0, "tc_fast": 9.0 / 8.0, "tc_auto": 9.0 / 8.0}
-# dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch, per read (ncu --set full capture of a
-# 2^20-read launch, profiles/r1_ncu_tc_exact_summary.txt: 123.42 MB read + 8.42 MB written)
-NCU_DRAM_BYTES_PER_READ = (123.416576e6 + 8.417536e6) / 1048576
+# dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch (ncu --set full capture of this bench's own launch
+# size, 2^22 reads x 100 bp, profiles/r1_ncu_tc_exact_4m_summary.txt: 499.64 MB read + 35.11 MB written)
+NCU_DRAM_BYTES_PER_READ = (499.643136e6 + 35.113728e6) / 4194304
 MUFU_PER_READ = {"fp32": 10 * 128 * READ_LEN, "tc_exact": 7 * 128 * READ_LEN, "tc_fast": 5 * 128 * READ_LEN,
                  "tc_auto": 5 * 128 * READ_LEN}
 XU_LANES_PER_CLK_PER_SM = 16          # measured, tools/tc_rate.cu
@@ -313,8 +313,8 @@ def run_ours(args, rank, world, local_rank):
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"],
                          "traffic": NCU_DRAM_BYTES_PER_READ * n if args.precision == "tc_exact" and READ_LEN == 100 else None,
-                         "traffic_note": "bytes per launch, scaled from the ncu capture of a 2^20-read launch; algorithmic "
-                                         "bytes per launch = %d (sequence + offset + slot plan/perm read, logits written)" % (n * (READ_LEN + 8 + 8 + 8)),
+                         "traffic_note": "bytes per launch from the ncu --set full capture of a 2^22-read launch (scaled per read for "
+                                         "other sizes); algorithmic bytes per launch = %d (sequence + offset + slot plan/perm read, logits written)" % (n * (READ_LEN + 8 + 8 + 8)),
                          "executed_tflops": achieved * EXECUTED_PER_ALGORITHMIC[args.precision],
                          "executed_frac": achieved * EXECUTED_PER_ALGORITHMIC[args.precision] / peaks["tflops"],
                          "peak_source": peaks["source"], "launch_ms": lstm_avg_s * 1000.0,
