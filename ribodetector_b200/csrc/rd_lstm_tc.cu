@@ -39,6 +39,9 @@ __device__ unsigned long long g_tc_prof[16];
 #define PROF_ADD(x)
 #endif
 
+#ifndef RD_TC_EXACT_EARLY_MAIN
+#define RD_TC_EXACT_EARLY_MAIN 1
+#endif
 #ifndef RD_TC_G_FAST
 #define RD_TC_G_FAST 4
 #endif
@@ -428,10 +431,21 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                             // Accumulate the 16 small correction products first (|W_lo.h_hi|, |W_hi.h_lo| ~ 2^-11 |z|),
                             // then the input chunk and the 8 large products: the tensor core's fp32 accumulator then
                             // rounds at large magnitude 9 times instead of 25 (measured: 1.6x lower logit error at
-                            // 100 bp, 2.4x at 300 bp).  In the wavefront chunk (mc == 0) the corrections trail the
-                            // activation warps K-chunk by K-chunk; the large pass follows the last h_ready.
+                            // 100 bp, 2.4x at 300 bp).  In the wavefront chunk (mc == 0) everything that depends only on
+                            // K-chunks 0..5 of h_t — their corrections, the input chunk, their large products — is
+                            // issued while the activation warps still work on the step's last chunk (which produces
+                            // K-chunks 6, 7); only 4 corrections + 2 large products follow the last h_ready, instead
+                            // of 2 + 1 + 8.  (RD_TC_EXACT_EARLY_MAIN=0 restores "all corrections, then all large".)
+                            constexpr int KSPLIT = (RD_TC_EXACT_EARLY_MAIN != 0) ? 6 : KCHUNKS;
+                            const int ksplit = mc == 0 ? KSPLIT : KCHUNKS;
 #pragma unroll
                             for (int kc = 0; kc < KCHUNKS; ++kc) {
+                                if (kc == ksplit && elected) {                // (mc == 0 only) early input chunk + large products
+                                    mma_ss<CG>(d, xdesc, xb, idesc, 1u);
+#pragma unroll
+                                    for (int k2 = 0; k2 < KSPLIT; ++k2)
+                                        mma_ts<CG>(d, abuf + 8 * k2, make_desc(s_hi + 2 * k2 * C::LBO + boff, C::LBO, 128), idesc, 1u);
+                                }
                                 if (mc == 0 && kc > 0) {
                                     PROF_T0();
                                     mbar_wait_cluster(bar_h + 8 * kc, hcnt & 1);
@@ -446,10 +460,11 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                                 }
                             }
                             if (elected) {
-                                mma_ss<CG>(d, xdesc, xb, idesc, 1u);
+                                if (ksplit == KCHUNKS) mma_ss<CG>(d, xdesc, xb, idesc, 1u);
 #pragma unroll
                                 for (int kc = 0; kc < KCHUNKS; ++kc)
-                                    mma_ts<CG>(d, abuf + 8 * kc, make_desc(s_hi + 2 * kc * C::LBO + boff, C::LBO, 128), idesc, 1u);
+                                    if (kc >= ksplit || ksplit == KCHUNKS)
+                                        mma_ts<CG>(d, abuf + 8 * kc, make_desc(s_hi + 2 * kc * C::LBO + boff, C::LBO, 128), idesc, 1u);
                             }
                         } else {
                             // input projection + biases (A from shared memory): overwrites D
