@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librd_b200.so")
+LIB_PATH = os.environ.get("RD_B200_LIB") or os.path.join(_HERE, "librd_b200.so")     # (RD_B200_LIB: A/B builds, tools/)
 
 RD_OK, RD_ERR_INVALID, RD_ERR_CUDA, RD_ERR_EMPTY_READ, RD_ERR_NOMEM, RD_ERR_UNSUPPORTED, RD_ERR_PARSE = range(7)
 FMT = {"fastq": 0, "fasta": 1}
