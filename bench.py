@@ -38,8 +38,8 @@ READ_LEN = 100
 # tensor FLOPs EXECUTED per algorithmic FLOP: K = 128 + 16 input chunk, x3 passes for the fp16 split
 EXECUTED_PER_ALGORITHMIC = {"fp32": 1.0, "tc_exact": 25.0 / 8.0, "tc_fast": 9.0 / 8.0, "tc_auto": 9.0 / 8.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch (ncu --set full capture of this bench's own launch
-# size, 2^22 reads x 100 bp, profiles/r1_ncu_tc_exact_4m_summary.txt: 499.64 MB read + 35.11 MB written)
-NCU_DRAM_BYTES_PER_READ = (499.643136e6 + 35.113728e6) / 4194304
+# size, 2^22 reads x 100 bp, profiles/r1_ncu_tc_exact_4m_summary.txt: 499.07 MB read + 34.44 MB written)
+NCU_DRAM_BYTES_PER_READ = (499.070720e6 + 34.439168e6) / 4194304
 MUFU_PER_READ = {"fp32": 10 * 128 * READ_LEN, "tc_exact": 7 * 128 * READ_LEN, "tc_fast": 5 * 128 * READ_LEN,
                  "tc_auto": 5 * 128 * READ_LEN}
 XU_LANES_PER_CLK_PER_SM = 16          # measured, tools/tc_rate.cu
