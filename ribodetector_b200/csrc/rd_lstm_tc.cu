@@ -282,13 +282,16 @@ __device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo
         const float A = ex2_mufu(fminf(zi, EXACT_CLAMP));
         const float B = ex2_mufu(fminf(zg, EXACT_CLAMP));
         const float F = ex2_mufu(fminf(zf, EXACT_CLAMP));
-        const float P = (1.0f + A) * (1.0f + B);
+        const float B1 = 1.0f + B;
+        const float P = fmaf(A, B1, B1);                          // (1+A)(1+B)
         const float Q = 1.0f + F;
-        const float num = fmaf(c_old, P, (1.0f - B) * Q);
+        const float num = fmaf(c_old, P, fmaf(-B, Q, Q));         // c (1+A)(1+B) + (1-B)(1+F)
         c_new = num * rcp_mufu(Q * P);
         const float O = ex2_mufu(fminf(zo, EXACT_CLAMP));
         const float D = ex2_mufu(fminf(EXACT_SCALE_G * c_new, EXACT_CLAMP));
-        h_new = (1.0f - D) * (EXACT_FMA_RCP ? rcp_fma((1.0f + O) * (1.0f + D)) : rcp_mufu((1.0f + O) * (1.0f + D)));
+        const float D1 = 1.0f + D;
+        const float den = fmaf(O, D1, D1);                        // (1+O)(1+D)
+        h_new = (1.0f - D) * (EXACT_FMA_RCP ? rcp_fma(den) : rcp_mufu(den));
     } else {
         const float ig = fmaf(tanh_mufu(zi), 0.5f, 0.5f);
         const float fg = FAST_FMA_FORGET ? sigmoid_fma(zf) : fmaf(tanh_mufu(zf), 0.5f, 0.5f);
