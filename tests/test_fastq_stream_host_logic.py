@@ -149,3 +149,38 @@ def test_error_paths(tmp_path):
     st = FastqGpuStream([HostStandIn()], [str(tmp_path / "empty.fq")], 100)
     st.run(sinks)
     assert st.num_seqs == 0
+
+
+def test_randomised_blocks_against_a_line_parser(tmp_path):
+    """200 random small files (CRLF, trailing blanks, no final newline, a truncated last record) x random block sizes:
+    the pipeline's output equals what the reference's four-line state machine (fastx_parser.py:15-47) would route."""
+    rng = np.random.default_rng(11)
+    for case in range(200):
+        n = int(rng.integers(0, 40))
+        recs, lines = [], []
+        for i in range(n):
+            L = int(rng.integers(1, 30))
+            seq = "".join(rng.choice(list("ACGTN"), size=L))
+            rec = ("@r%d" % i + (" x" if rng.random() < 0.3 else ""), seq, "+" + ("r%d" % i if rng.random() < 0.2 else ""),
+                   "".join(chr(int(c)) for c in rng.integers(33, 74, size=L)))
+            recs.append(rec)
+            for ln in rec:
+                lines.append(ln + (" " if rng.random() < 0.1 else "") + ("\r\n" if rng.random() < 0.2 else "\n"))
+        text = "".join(lines)
+        if n and rng.random() < 0.3:
+            text = text.rstrip("\r\n ")                                   # no final newline (the record still counts)
+            recs[-1] = tuple(x.rstrip() for x in recs[-1])
+        if rng.random() < 0.3 and (not text or text.endswith("\n")):
+            text += "@cut\nACGT\n+"                                        # truncated final record: dropped
+        p = tmp_path / ("c%d.fq" % case)
+        p.write_bytes(text.encode())
+        block = int(rng.integers(64, 600))
+        longest = max([len(l) for l in lines] + [1]) * 4 + 16
+        block = max(block, longest)
+        with open(tmp_path / "n", "wb") as fn, open(tmp_path / "r", "wb") as fr:
+            st = FastqGpuStream([HostStandIn(), HostStandIn()], [str(p)], 100, block_bytes=block, threads=1)
+            st.run({"non": [fn], "rrna": [fr], "unc": None})
+        labels = [_label_rule(r[1]) for r in recs]
+        assert (tmp_path / "n").read_bytes() == _expect(recs, labels, 0), (case, block)
+        assert (tmp_path / "r").read_bytes() == _expect(recs, labels, 1), (case, block)
+        assert st.num_seqs == n
