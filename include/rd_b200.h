@@ -188,6 +188,16 @@ const char* rd_fastx_last_error(void);
  * BGZF member (use a serial gzip reader), -RD_ERR_PARSE on a corrupt member. */
 int64_t rd_bgzf_inflate(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap, int64_t* in_used, int threads);
 
+/* The serial form for any other .gz (members cannot be located without inflating): a zlib stream driven directly on the
+ * caller's buffers, concatenated members and zero padding handled, CRC-32 checked.  rd_gz_inflate returns the bytes
+ * written into out (stops when in or out is exhausted), *in_used = input consumed, *mid_member = 1 while inside a member
+ * (end of file there = truncated file); -RD_ERR_PARSE on a corrupt stream (message from rd_fastx_last_error). */
+typedef struct rd_gz rd_gz;
+rd_gz* rd_gz_open(void);
+int64_t rd_gz_inflate(rd_gz* g, const uint8_t* in, int64_t in_len, int64_t* in_used, uint8_t* out, int64_t out_cap,
+                      int* mid_member);
+void rd_gz_close(rd_gz* g);
+
 /* ---- the same edges on the device, for uncompressed FASTQ text resident in HBM --------------------------
  * K0.  Replaces seq_parser's FASTQ branch (fastx_parser.py:15-47) with rd_scan_fastx's semantics: d_buf[0..len)
  * (16-byte aligned) is scanned in one pass; d_rec receives int64[8] per record = [begin, end) of the header,

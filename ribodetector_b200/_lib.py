@@ -40,6 +40,9 @@ SIGNATURES = {
     "rd_partition_records": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rd_fastx_last_error": (_c.c_char_p, []),
     "rd_bgzf_inflate": (_i64, [_vp, _i64, _vp, _i64, _vp, _i]),
+    "rd_gz_open": (_vp, []),
+    "rd_gz_inflate": (_i64, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "rd_gz_close": (None, [_vp]),
     "rd_scan_fastq_device": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp, _vp]),
     "rd_classify_records": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rd_partition_records_device": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

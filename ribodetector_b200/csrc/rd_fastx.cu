@@ -350,3 +350,64 @@ extern "C" int64_t rd_bgzf_inflate(const uint8_t* in, int64_t in_len, uint8_t* o
     *in_used = ip;
     return op;
 }
+
+// ---- serial gzip stream (any .gz that is not BGZF-framed): zlib driven directly on the caller's buffers — no
+// intermediate bytes objects, CRC-32 checked inside zlib, concatenated members handled.  Replaces `gzip.open`
+// (seq_encoder.py:43-53) where the members cannot be located without inflating.
+struct rd_gz { z_stream zs; bool in_member; };
+
+extern "C" rd_gz* rd_gz_open(void) {
+    rd_gz* g = new (std::nothrow) rd_gz();
+    if (!g) return nullptr;
+    memset(&g->zs, 0, sizeof(g->zs));
+    if (inflateInit2(&g->zs, 15 + 16) != Z_OK) { delete g; return nullptr; }
+    g->in_member = false;
+    return g;
+}
+
+extern "C" void rd_gz_close(rd_gz* g) {
+    if (!g) return;
+    inflateEnd(&g->zs);
+    delete g;
+}
+
+// Inflates from in[0..in_len) into out[0..out_cap) until either is exhausted.  Returns the bytes written (>= 0) or
+// -RD_ERR_PARSE; *in_used = input consumed; *mid_member = 1 if the stream stands inside a member (so end of file here
+// means a truncated file).  Zero padding between / after members is skipped like Python's gzip module does.
+extern "C" int64_t rd_gz_inflate(rd_gz* g, const uint8_t* in, int64_t in_len, int64_t* in_used, uint8_t* out,
+                                 int64_t out_cap, int* mid_member) {
+    g_fx_err.clear();
+    if (!g || in_len < 0 || out_cap < 0 || !in_used || (in_len && !in) || (out_cap && !out)) {
+        g_fx_err = "rd_gz_inflate: bad arguments";
+        return -RD_ERR_INVALID;
+    }
+    int64_t ip = 0, op = 0;
+    while (ip < in_len && op < out_cap) {
+        if (!g->in_member) {
+            while (ip < in_len && in[ip] == 0) ++ip;                  // padding between members
+            if (ip == in_len) break;
+            g->in_member = true;
+        }
+        const int64_t ni = std::min<int64_t>(in_len - ip, 1 << 30), no = std::min<int64_t>(out_cap - op, 1 << 30);
+        g->zs.next_in = const_cast<Bytef*>(in + ip);
+        g->zs.avail_in = (uInt)ni;
+        g->zs.next_out = out + op;
+        g->zs.avail_out = (uInt)no;
+        const int rc = inflate(&g->zs, Z_NO_FLUSH);
+        ip += ni - (int64_t)g->zs.avail_in;
+        op += no - (int64_t)g->zs.avail_out;
+        if (rc == Z_STREAM_END) {
+            g->in_member = false;
+            if (inflateReset(&g->zs) != Z_OK) { g_fx_err = "gzip: inflateReset failed"; return -RD_ERR_PARSE; }
+        } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+            g_fx_err = std::string("gzip: corrupt stream (") + (g->zs.msg ? g->zs.msg : "inflate failed") + ")";
+            return -RD_ERR_PARSE;
+        } else if (rc == Z_BUF_ERROR && g->zs.avail_in != 0 && g->zs.avail_out != 0) {
+            g_fx_err = "gzip: inflate made no progress";
+            return -RD_ERR_PARSE;
+        }
+    }
+    *in_used = ip;
+    if (mid_member) *mid_member = g->in_member ? 1 : 0;
+    return op;
+}

@@ -166,13 +166,65 @@ class BgzfReader:
         self.fh.close()
 
 
+class GzStreamReader:
+    """File-like reader (readinto / close) of any other .gz: zlib driven by `rd_gz_inflate` straight into the caller's
+    buffer (no intermediate bytes objects; concatenated members, zero padding and CRC-32 handled like `gzip.open`)."""
+
+    COMP = 8 << 20
+
+    def __init__(self, path):
+        self.fh = open(path, "rb", buffering=0)
+        self.lib = _lib.load_library()
+        self.g = ctypes.c_void_p(self.lib.rd_gz_open())
+        if not self.g:
+            raise MemoryError("rd_gz_open failed")
+        self.comp = np.empty(self.COMP, np.uint8)
+        self.lo = self.hi = 0
+        self.raw_eof = False
+        self.mid = ctypes.c_int(0)
+
+    def readinto(self, b):
+        out = np.frombuffer(b, np.uint8)
+        pos = 0
+        used = ctypes.c_int64(0)
+        while pos < out.size:
+            if self.lo == self.hi and not self.raw_eof:
+                k = self.fh.readinto(memoryview(self.comp))
+                self.lo, self.hi = 0, k or 0
+                self.raw_eof = not k
+            if self.lo == self.hi:
+                if self.mid.value:
+                    raise EOFError("Compressed file ended before the end-of-stream marker was reached")
+                break
+            n = self.lib.rd_gz_inflate(self.g, ctypes.c_void_p(self.comp.ctypes.data + self.lo), self.hi - self.lo,
+                                       ctypes.byref(used), ctypes.c_void_p(out.ctypes.data + pos), out.size - pos,
+                                       ctypes.byref(self.mid))
+            if n < 0:
+                raise ValueError(self.lib.rd_fastx_last_error().decode("utf-8", "replace"))
+            self.lo += used.value
+            pos += n
+        return pos
+
+    def close(self):
+        self.fh.close()
+        if self.g:
+            self.lib.rd_gz_close(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                    # noqa: BLE001
+            pass
+
+
 def open_text(path, gz, threads=8):
-    """Binary reader of a sequence file's TEXT: the file itself, a parallel BGZF reader, or Python's gzip."""
+    """Binary reader of a sequence file's TEXT: the file itself, a parallel BGZF reader, or a zlib stream reader."""
     if not gz:
         return open(path, "rb", buffering=0)
     if BgzfReader.sniff(path):
         return BgzfReader(path, threads)
-    return gzip.open(path, "rb")
+    return GzStreamReader(path)
 
 
 def _host_array(n, dtype, pinned):

@@ -252,3 +252,45 @@ def test_fastx_reader_takes_bgzf_input(tmp_path, golden):
     p = tmp_path / "g.fq.gz"
     p.write_bytes(_bgzf_bytes(case["text"].encode("latin-1"), block=37))
     assert _read_all(str(p), block_bytes=64) == [tuple(r) for r in case["records"]]
+
+
+def test_gz_stream_reader_matches_gzip_module(tmp_path):
+    from ribodetector_b200.data_loader import GzStreamReader, open_text
+    rng = np.random.default_rng(5)
+    text = bytes(rng.choice(list(b"ACGTN\n@+I"), size=3_000_000).tolist())
+
+    def read_all(path, step):
+        r = open_text(str(path), True)
+        assert isinstance(r, GzStreamReader)
+        got, buf = bytearray(), np.empty(step, np.uint8)
+        while True:
+            k = r.readinto(memoryview(buf))
+            if not k:
+                break
+            got += buf[:k].tobytes()
+        r.close()
+        return bytes(got)
+
+    one = tmp_path / "one.fq.gz"
+    with gzip.open(one, "wb") as f:
+        f.write(text)
+    multi = tmp_path / "multi.fq.gz"                      # concatenated members (what ParallelGzipWriter writes), zero padding
+    multi.write_bytes(gzip.compress(text[:1_000_000]) + gzip.compress(text[1_000_000:2_500_000]) + b"\0" * 37
+                      + gzip.compress(text[2_500_000:]) + b"\0" * 512)
+    with open_for_write(str(tmp_path / "ours.fq.gz"), 3) as f:
+        f.write(text)
+    empty = tmp_path / "empty.fq.gz"
+    empty.write_bytes(gzip.compress(b""))
+    for step in (1 << 22, 65537, 100):
+        assert read_all(one, step) == text
+        assert read_all(multi, step) == text
+        assert read_all(tmp_path / "ours.fq.gz", step) == text
+        assert read_all(empty, step) == b""
+    (tmp_path / "cut.fq.gz").write_bytes(one.read_bytes()[:-100])
+    with pytest.raises(EOFError):
+        read_all(tmp_path / "cut.fq.gz", 1 << 20)
+    bad = bytearray(one.read_bytes())
+    bad[len(bad) // 2] ^= 0xFF
+    (tmp_path / "bad.fq.gz").write_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        read_all(tmp_path / "bad.fq.gz", 1 << 20)
