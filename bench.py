@@ -36,12 +36,13 @@ import numpy as np  # noqa: E402
 
 READ_LEN = 100
 # tensor FLOPs EXECUTED per algorithmic FLOP: K = 128 + 16 input chunk, x3 passes for the fp16 split
-EXECUTED_PER_ALGORITHMIC = {"fp32": 1.0, "tc_exact": 25.0 / 8.0, "tc_fast": 9.0 / 8.0, "tc_auto": 9.0 / 8.0}
+EXECUTED_PER_ALGORITHMIC = {"fp32": 1.0, "tc_exact": 25.0 / 8.0, "tc_fast": 9.0 / 8.0, "tc_auto": 9.0 / 8.0,
+                            "tc_mixed": 17.0 / 8.0}      # MMA issue slots (an 8-bit K=32 MMA costs what an fp16 K=16 one does)
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch (ncu --set full capture of this bench's own launch
 # size, 2^22 reads x 100 bp, profiles/r1_ncu_tc_exact_4m_summary.txt: 499.07 MB read + 34.44 MB written)
 NCU_DRAM_BYTES_PER_READ = (499.070720e6 + 34.439168e6) / 4194304
 MUFU_PER_READ = {"fp32": 10 * 128 * READ_LEN, "tc_exact": 7 * 128 * READ_LEN, "tc_fast": 5 * 128 * READ_LEN,
-                 "tc_auto": 5 * 128 * READ_LEN}
+                 "tc_auto": 5 * 128 * READ_LEN, "tc_mixed": 7 * 128 * READ_LEN}
 XU_LANES_PER_CLK_PER_SM = 16          # measured, tools/tc_rate.cu
 BATCH_READS = 1 << 22
 FLOP_PER_READ = 131072 * READ_LEN + 1024          # n*2*128*512 + 2*256*2
@@ -297,7 +298,8 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tc_exact": "f16x2-split/f32-acc", "tc_fast": "f16/f32-acc",
-                      "tc_auto": "f16/f32-acc + f16x2-split/f32-acc on low-margin reads"}[args.precision],
+                      "tc_auto": "f16/f32-acc + f16x2-split/f32-acc on low-margin reads",
+                      "tc_mixed": "f16 + e5m2 corrections/f32-acc"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "100 bp single-end, 50M synthetic reads per B200 (BASELINE configs[1]): "
                                    "timed as %d batches of %d reads on each of %d GPU(s)" % (args.steps, n, world),
@@ -357,7 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RD_BENCH_PRECISION", "tc_exact"),
-                    choices=["fp32", "tc_exact", "tc_fast", "tc_auto"])
+                    choices=["fp32", "tc_exact", "tc_fast", "tc_auto", "tc_mixed"])
     ap.add_argument("--reads-per-step", type=int, default=BATCH_READS)
     ap.add_argument("--cpu-batches", type=int, default=28, help="1024-read batches per CPU worker in cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")

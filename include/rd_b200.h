@@ -64,6 +64,12 @@ typedef struct rd_handle rd_handle;
  *              reads): LABELS equal TC_EXACT's, logits are exact-grade inside the band and fast-grade
  *              (|dlogit| <= 5e-2 * max(1, max_len/100)) outside it                                    */
 #define RD_PREC_TC_AUTO  3
+/*   TC_MIXED : the TC_EXACT structure with the two correction passes in tcgen05 kind::f8f6f4 (e5m2, K = 32 per
+ *              MMA): fp16 main pass + one 8-bit pass over [W_lo | W_hi] . [h_hi ; h_lo] = 17 MMAs per chunk
+ *              instead of 25, same few-ulp ex2/rcp activations.  |dlogit| <= 2e-3 * max(1, max_len/100),
+ *              |dprob| <= 1e-3 (SURVEY.md 8c's tolerance), labels identical outside |margin| <= 4e-3 * max(1, max_len/100) */
+#define RD_PREC_TC_MIXED 4
+#define RD_PREC_LAST     RD_PREC_TC_MIXED
 
 /* paired-end combination, detect.py:616-663 (`-e/--ensure`) */
 #define RD_PAIR_NONE   0   /* argmax(logits_r1 + logits_r2)            detect.py:655-661 */

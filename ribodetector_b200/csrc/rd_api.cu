@@ -275,7 +275,7 @@ extern "C" int rd_classify(rd_handle* h, const uint8_t* d_seq, const int64_t* d_
     if (rc) return rc;
     if (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED)
         return fail(h, RD_ERR_INVALID, "rd_classify: unknown semantics");
-    if (precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO)
+    if (precision < RD_PREC_FP32 || precision > RD_PREC_LAST)
         return fail(h, RD_ERR_INVALID, "rd_classify: unknown precision");
     if (n == 0) return RD_OK;
     if (!d_off || !d_logits) return fail(h, RD_ERR_INVALID, "rd_classify: d_off and d_logits are required");
@@ -343,7 +343,7 @@ static int classify_host_impl(rd_handle* h, int ends,
     if (rc) return rc;
     if (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED)
         return fail(h, RD_ERR_INVALID, "rd_classify_host: unknown semantics");
-    if (precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO)
+    if (precision < RD_PREC_FP32 || precision > RD_PREC_LAST)
         return fail(h, RD_ERR_INVALID, "rd_classify_host: unknown precision");
     if (ends == 2 && (mode < RD_PAIR_NONE || mode > RD_PAIR_BOTH))
         return fail(h, RD_ERR_INVALID, "rd_classify_pairs_host: unknown mode");

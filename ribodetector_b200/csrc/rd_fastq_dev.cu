@@ -475,7 +475,7 @@ extern "C" int rd_classify_records(rd_handle* h, const uint8_t* d_buf, const int
                                    int64_t* d_counts, void* stream) {
     if (!h) return RD_ERR_INVALID;
     if (n < 0 || n > ((int64_t)1 << 30) || max_len < 1 || max_len > RD_MAX_LEN ||
-        (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED) || precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO)
+        (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED) || precision < RD_PREC_FP32 || precision > RD_PREC_LAST)
         return fq_fail(h, RD_ERR_INVALID, "rd_classify_records: bad arguments");
     if (n == 0) return RD_OK;
     if (!d_buf || !d_rec || !d_logits) return fq_fail(h, RD_ERR_INVALID, "rd_classify_records: NULL buffer");
@@ -504,7 +504,7 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
     if (slot < 0 || slot >= rd_fq_state::NSLOT || (ends != 1 && ends != 2) || len1 < 0 || (ends == 2 && len2 < 0) ||
         max_records < 1 || max_records > ((int64_t)1 << 30) || max_len < 1 || max_len > RD_MAX_LEN || !n_records ||
         !consumed2 || !out_bytes2 || (len1 && !buf1) || (ends == 2 && len2 && !buf2) || !out1 || (ends == 2 && !out2) ||
-        (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED) || precision < RD_PREC_FP32 || precision > RD_PREC_TC_AUTO ||
+        (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED) || precision < RD_PREC_FP32 || precision > RD_PREC_LAST ||
         (ends == 2 && (mode < RD_PAIR_NONE || mode > RD_PAIR_BOTH)))
         return fq_fail(h, RD_ERR_INVALID, "rd_fastq_submit: bad arguments");
     RD_CUDA(h, cudaSetDevice(h->device));

@@ -24,8 +24,15 @@
 //         W_hi and W_lo: 136 KB) and runs two tiles (M = 256) in lock step; three fp16 passes
 //         W_lo.h_hi + W_hi.h_lo + W_hi.h_hi (25 MMAs per chunk, small products first) with fp32
 //         accumulation; merged-denominator ex2/rcp activations accurate to a few ulp.
+// MIXED : the EXACT structure with the two correction passes in kind::f8f6f4 (e5m2, K = 32 per MMA): the fp16 main
+//         pass W_hi.h_hi plus ONE 8-bit pass over K = 256, [W_lo8 | W_hi8] . [h_hi8 ; h_lo8], i.e. 17 MMAs per chunk
+//         instead of 25.  The corrections are ~2^-12 of the products, so 3 significant bits keep them to ~2^-15:
+//         |dlogit| <= 2e-3 at 100 bp (measured ~1e-3 worst case, tests/test_gpu_parity.py), |dp| <= 1e-3.
+//         h is carried as h * 2^-6 (free: the scale rides in the cell's last FMA) and W_hh as W * 2^6, which
+//         puts h_hi (as the top byte of its fp16), the fp16 residuals and the weights in e5m2's normal range.
 // See DESIGN.md for the layout tables and the roofline arithmetic.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "rd_common.cuh"
 
 #ifdef RD_TC_PROFILE
@@ -62,15 +69,19 @@ constexpr int KG_H = 16;                              // 8-wide k-groups of h
 constexpr int KG_X = 2;                               // k-groups of the one-hot/bias chunk
 constexpr int X_BYTES = 2 * RD_TILE * 16;             // one x buffer: [2 k-groups][128 rows][16 B]
 
-template <bool EXACT>
+enum { M_FAST = 0, M_EXACT = 1, M_MIXED = 2 };
+
+template <int MODE>
 struct Cfg {
+    static constexpr bool EXACT = MODE != M_FAST;                 // two weight images, CTA pair (EXACT and MIXED)
     static constexpr int CG = EXACT ? 2 : 1;                      // CTAs per MMA (cta_group)
     static constexpr int NL = RD_G4 / CG;                         // weight rows resident per CTA
     static constexpr int NB = MMA_N / CG;                         // weight rows per CTA per MMA chunk
     static constexpr int HI_BYTES = (KG_H + KG_X) * NL * 16;      // FAST 147456, EXACT 73728
-    static constexpr int LO_BYTES = EXACT ? KG_H * NL * 16 : 0;   // EXACT 65536
+    static constexpr int LO_BYTES = EXACT ? KG_H * NL * 16 : 0;   // EXACT 65536 (fp16, K = 128); MIXED 65536 (e5m2, K = 256)
     static constexpr int LBO = NL * 16;                           // bytes between k-groups
-    // tensor memory: A buffer s at column s*ACOLS = [h_hi 64 | h_lo 64 (EXACT)]; D ring at DCOL0
+    // tensor memory: A buffer s at column s*ACOLS = [h_hi 64 | h_lo 64 (EXACT)] or [h_hi 64 | h_hi8 32 | h_lo8 32 (MIXED)];
+    // D ring at DCOL0
     static constexpr int ACOLS = EXACT ? 128 : 64;
     static constexpr int DCOL0 = 256;
     static constexpr int M = 128 * CG;
@@ -153,6 +164,10 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
                  "r"(d) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE (layout verified by tools/tc_probe.cu)
 //   byte(n, k) = (k/8)*LBO + (n/8)*SBO + (n%8)*16 + (k%8)*2 ; fields are in 16-byte units
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -164,6 +179,22 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// kind::f8f6f4: A and B format e5m2 (1) at bits 7 and 10; one MMA is K = 32 (two 16-byte k-groups; tools/tc_probe8.cu)
+__host__ __device__ constexpr uint32_t make_idesc8(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <int CG>
+__device__ __forceinline__ void mma_ts8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if constexpr (CG == 1) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
 template <int CG>
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     if constexpr (CG == 1) {
@@ -276,9 +307,13 @@ __device__ __forceinline__ float rcp_fma(float d) {
     r = fmaf(-d, y, 1.0f);
     return fmaf(y, r, y);
 }
-template <bool EXACT>
+// MIXED carries h as h * MIXED_HS (the weight image as W / MIXED_HS); the residual h - fp16(h) is scaled by MIXED_LS
+// before it is rounded to e5m2 (the W_hi8 image by 1 / MIXED_LS)
+constexpr float MIXED_HS = 0.015625f;                       // 2^-6
+constexpr float MIXED_LS = 16384.0f;                        // 2^14
+template <int MODE>
 __device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo, float c_old, float& c_new, float& h_new) {
-    if constexpr (EXACT) {
+    if constexpr (MODE != M_FAST) {
         const float A = ex2_mufu(fminf(zi, EXACT_CLAMP));
         const float B = ex2_mufu(fminf(zg, EXACT_CLAMP));
         const float F = ex2_mufu(fminf(zf, EXACT_CLAMP));
@@ -291,7 +326,8 @@ __device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo
         const float D = ex2_mufu(fminf(EXACT_SCALE_G * c_new, EXACT_CLAMP));
         const float D1 = 1.0f + D;
         const float den = fmaf(O, D1, D1);                        // (1+O)(1+D)
-        h_new = (1.0f - D) * (EXACT_FMA_RCP ? rcp_fma(den) : rcp_mufu(den));
+        const float hnum = MODE == M_MIXED ? fmaf(-MIXED_HS, D, MIXED_HS) : 1.0f - D;
+        h_new = hnum * (EXACT_FMA_RCP ? rcp_fma(den) : rcp_mufu(den));
     } else {
         const float ig = fmaf(tanh_mufu(zi), 0.5f, 0.5f);
         const float fg = FAST_FMA_FORGET ? sigmoid_fma(zf) : fmaf(tanh_mufu(zf), 0.5f, 0.5f);
@@ -305,6 +341,17 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// two e5m2 values in 16 bits, `lo` in the low byte (= the lower k index)
+__device__ __forceinline__ uint32_t e5m2x2_from_h2(uint32_t h2) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e5m2x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+    return r;
+}
+__device__ __forceinline__ uint32_t e5m2x2_from_f32(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // one-hot/bias chunk of a read at one step, k = [onehot4 (W_ih hi rows) | onehot4 (W_ih lo rows) | 1 | 1 | 0 x6]:
 // k-group 0 (this 16-byte row) changes per step, k-group 1 = {1, 1, 0...} is written once per kernel.
@@ -316,7 +363,7 @@ __device__ __forceinline__ void st_x_row(uint32_t saddr, uint32_t code) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
-template <bool EXACT, int G>
+template <int MODE, int G>
 __global__ void __launch_bounds__(tc_threads(G), 1)
 lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int ostride,   // the caller's reads
                const uint32_t* __restrict__ splan, const int32_t* __restrict__ perm, int L, int n_tiles_arg,
@@ -327,7 +374,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                const float* __restrict__ bout,         // [2]
                const float* __restrict__ revlut,       // [RD_MAX_LEN][5][2]
                float* __restrict__ logits) {
-    using C = Cfg<EXACT>;
+    using C = Cfg<MODE>;
+    constexpr bool EXACT = C::EXACT;                  // split precision on a CTA pair (M_EXACT and M_MIXED)
     constexpr int CG = C::CG;
     constexpr int EPI_WARPS = epi_warps(G), EPI_THREADS = EPI_WARPS * 32, TC_THREADS = tc_threads(G);
     constexpr int SUBS = 16 / G;                      // 8-unit groups per warp per step
@@ -366,7 +414,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
             for (int o = 0; o < C::LO_BYTES; o += 8192) bulk_g2s(s_lo + o, src_lo + o, 8192, bar_w);
         }
     }
-    for (int i = tid; i < 2 * RD_H; i += TC_THREADS) wout_s[i] = wout[(i >> 7) * 2 * RD_H + (i & 127)];   // fwd half of W_out
+    for (int i = tid; i < 2 * RD_H; i += TC_THREADS)      // fwd half of W_out (MIXED: the cell hands out h * MIXED_HS)
+        wout_s[i] = wout[(i >> 7) * 2 * RD_H + (i & 127)] * (MODE == M_MIXED ? 1.0f / MIXED_HS : 1.0f);
     if (tid < 2 * RD_TILE) {      // constant k-group 1 of both x buffers: k8 = k9 = 1.0 (bias hi / lo rows), rest 0
         const uint32_t a = s_x + (uint32_t)((tid >> 7) * X_BYTES + RD_TILE * 16 + (tid & 127) * 16);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(a), "r"(0x3C003C00u), "r"(0u) : "memory");
@@ -455,7 +504,16 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                                     tc_fence_after();
                                     PROF_ADD(pw_h);
                                 }
-                                if (elected) {
+                                if constexpr (MODE == M_MIXED) {
+                                    // 8-bit corrections, one K = 32 MMA per 32 hidden units (= K-chunks kc-1, kc) and term:
+                                    // W_lo8 . h_hi8 (image k-groups 0..7, A columns 64..95), W_hi8 . h_lo8 (8..15, 96..127)
+                                    if (elected && (kc & 1)) {
+                                        const int q8 = kc >> 1;
+                                        constexpr uint32_t idesc8 = make_idesc8(C::M, MMA_N);
+                                        mma_ts8<CG>(d, abuf + 64 + 8 * q8, make_desc(s_lo + 2 * q8 * C::LBO + boff, C::LBO, 128), idesc8, q8 > 0 ? 1u : 0u);
+                                        mma_ts8<CG>(d, abuf + 96 + 8 * q8, make_desc(s_lo + (8 + 2 * q8) * C::LBO + boff, C::LBO, 128), idesc8, 1u);
+                                    }
+                                } else if (elected) {
                                     const uint64_t bhi = make_desc(s_hi + 2 * kc * C::LBO + boff, C::LBO, 128);
                                     const uint64_t blo = make_desc(s_lo + 2 * kc * C::LBO + boff, C::LBO, 128);
                                     mma_ts<CG>(d, abuf + 8 * kc, blo, idesc, kc > 0 ? 1u : 0u);      // W_lo . h_hi
@@ -583,7 +641,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         float cn;
-                        lstm_cell<EXACT>(__uint_as_float(v[u]), __uint_as_float(v[8 + u]), __uint_as_float(v[16 + u]),
+                        lstm_cell<MODE>(__uint_as_float(v[u]), __uint_as_float(v[8 + u]), __uint_as_float(v[16 + u]),
                                          __uint_as_float(v[24 + u]), c[cc][u], cn, hv[u]);
                         if (active) c[cc][u] = cn;
                     }
@@ -597,7 +655,21 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                     }
                     if (more) {
                         const uint32_t hcol = awr + (uint32_t)(4 * j);
-                        if constexpr (EXACT) {
+                        if constexpr (MODE == M_MIXED) {
+                            // fp16(h'), its top byte pattern as e5m2 (h_hi8), and the residual h' - fp16(h') as e5m2 (h_lo8)
+                            uint32_t hi[4], hi8[4], lo8[4];
+#pragma unroll
+                            for (int p2 = 0; p2 < 4; ++p2) {
+                                __half2 h2 = __floats2half2_rn(hv[2 * p2], hv[2 * p2 + 1]);
+                                float2 back = __half22float2(h2);
+                                hi[p2] = *reinterpret_cast<uint32_t*>(&h2);
+                                hi8[p2] = e5m2x2_from_h2(hi[p2]);
+                                lo8[p2] = e5m2x2_from_f32((hv[2 * p2] - back.x) * MIXED_LS, (hv[2 * p2 + 1] - back.y) * MIXED_LS);
+                            }
+                            tmem_st4(hcol, hi[0], hi[1], hi[2], hi[3]);
+                            tmem_st2(awr + (uint32_t)(64 + 2 * j), hi8[0] | (hi8[1] << 16), hi8[2] | (hi8[3] << 16));
+                            tmem_st2(awr + (uint32_t)(96 + 2 * j), lo8[0] | (lo8[1] << 16), lo8[2] | (lo8[3] << 16));
+                        } else if constexpr (EXACT) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -671,11 +743,17 @@ inline int col_to_row(int n) { return ((n % 32) / 8) * RD_H + (n / 32) * 8 + (n 
 
 // image[rank][kg][n_local][8] halfs; MMA chunk cc takes rows cc*NB .. cc*NB+NB-1 of each rank,
 // which are D columns cc*128 + rank*NB + i  (cta_group::2: each CTA supplies half of the N columns).
-void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh, int cg,
-                  std::vector<__half>& hi, std::vector<__half>& lo, bool exact) {
+// lo (bytes): M_EXACT  [rank][kg 0..15][n_local][8] halfs  = fp16(W - W_hi)
+//             M_MIXED  [rank][kg 0..15][n_local][16] e5m2: k-groups 0..7 = e5m2(W' - fp16(W')) for k = 16 kg + i,
+//                      k-groups 8..15 = e5m2(fp16(W') / MIXED_LS), with W' = W / MIXED_HS (see lstm_cell)
+void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh, int mode,
+                  std::vector<__half>& hi, std::vector<uint8_t>& lo) {
+    const bool exact = mode != M_FAST;
+    const int cg = exact ? 2 : 1;
     const int NL = RD_G4 / cg, NB = MMA_N / cg;
     hi.assign((size_t)cg * (KG_H + KG_X) * NL * 8, __float2half(0.f));
-    lo.assign(exact ? (size_t)cg * KG_H * NL * 8 : 0, __float2half(0.f));
+    lo.assign(exact ? (size_t)cg * KG_H * NL * 16 : 0, 0);
+    __half* lo16 = reinterpret_cast<__half*>(lo.data());
     for (int rank = 0; rank < cg; ++rank)
         for (int nl = 0; nl < NL; ++nl) {
             const int cc = nl / NB, i = nl % NB;
@@ -686,14 +764,20 @@ void build_images(const float* w_hh, const float* w_ih, const float* b_ih, const
             const bool is_g = gate == 2;
             const double sc = exact ? (is_g ? (double)EXACT_SCALE_G : (double)EXACT_SCALE_IFO)
                                     : (is_g ? 1.0 : (gate == 1 && FAST_FMA_FORGET) ? (double)EXACT_SCALE_IFO : 0.5);
+            const double hs = mode == M_MIXED ? 1.0 / (double)MIXED_HS : 1.0;       // h is carried as h * MIXED_HS
             for (int k = 0; k < RD_H; ++k) {
-                const float w = (float)(sc * (double)w_hh[row * RD_H + k]);
+                const float w = (float)(sc * hs * (double)w_hh[row * RD_H + k]);
                 const __half whi = __float2half_rn(w);
                 const size_t at = (((size_t)rank * (KG_H + KG_X) + k / 8) * NL + nl) * 8 + k % 8;
                 hi[at] = whi;
-                if (exact) {
+                if (mode == M_EXACT) {
                     const size_t al = (((size_t)rank * KG_H + k / 8) * NL + nl) * 8 + k % 8;
-                    lo[al] = __float2half_rn(w - __half2float(whi));
+                    lo16[al] = __float2half_rn(w - __half2float(whi));
+                } else if (mode == M_MIXED) {
+                    const size_t a_lo = (((size_t)rank * KG_H + k / 16) * NL + nl) * 16 + k % 16;
+                    const size_t a_hi = (((size_t)rank * KG_H + 8 + k / 16) * NL + nl) * 16 + k % 16;
+                    lo[a_lo] = (uint8_t)__nv_cvt_float_to_fp8(w - __half2float(whi), __NV_SATFINITE, __NV_E5M2);
+                    lo[a_hi] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(whi) / MIXED_LS, __NV_SATFINITE, __NV_E5M2);
                 }
             }
             // x chunk: k = 0..3 W_ih hi, 4..7 W_ih lo, 8 bias hi, 9 bias lo
@@ -718,24 +802,34 @@ constexpr int G_FAST = RD_TC_G_FAST, G_EXACT = RD_TC_G_EXACT;
 
 struct rd_tc_state {
     uint8_t* d_img_fast = nullptr;      // [1][147456]
-    uint8_t* d_img_hi = nullptr;        // [2][73728]
+    uint8_t* d_img_hi = nullptr;        // [2][73728]   M_EXACT
     uint8_t* d_img_lo = nullptr;        // [2][65536]
-    bool attr_fast = false, attr_exact = false;
+    uint8_t* d_img_mhi = nullptr;       // [2][73728]   M_MIXED
+    uint8_t* d_img_mlo = nullptr;       // [2][65536]
+    bool attr_fast = false, attr_exact = false, attr_mixed = false;
 };
+
+static int upload(rd_handle* h, uint8_t** dst, const void* src, size_t bytes) {
+    RD_CUDA(h, cudaMalloc(dst, bytes));
+    RD_CUDA(h, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return RD_OK;
+}
 
 int rd_tc_create(rd_handle* h, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh) {
     rd_tc_state* s = new (std::nothrow) rd_tc_state();
     if (!s) { h->err = "rd_tc_create: out of host memory"; return RD_ERR_NOMEM; }
     h->tc = s;
-    std::vector<__half> hi, lo;
-    build_images(w_hh, w_ih, b_ih, b_hh, 1, hi, lo, false);
-    RD_CUDA(h, cudaMalloc(&s->d_img_fast, hi.size() * sizeof(__half)));
-    RD_CUDA(h, cudaMemcpy(s->d_img_fast, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    build_images(w_hh, w_ih, b_ih, b_hh, 2, hi, lo, true);
-    RD_CUDA(h, cudaMalloc(&s->d_img_hi, hi.size() * sizeof(__half)));
-    RD_CUDA(h, cudaMalloc(&s->d_img_lo, lo.size() * sizeof(__half)));
-    RD_CUDA(h, cudaMemcpy(s->d_img_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    RD_CUDA(h, cudaMemcpy(s->d_img_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    std::vector<__half> hi;
+    std::vector<uint8_t> lo;
+    int rc;
+    build_images(w_hh, w_ih, b_ih, b_hh, M_FAST, hi, lo);
+    if ((rc = upload(h, &s->d_img_fast, hi.data(), hi.size() * sizeof(__half)))) return rc;
+    build_images(w_hh, w_ih, b_ih, b_hh, M_EXACT, hi, lo);
+    if ((rc = upload(h, &s->d_img_hi, hi.data(), hi.size() * sizeof(__half)))) return rc;
+    if ((rc = upload(h, &s->d_img_lo, lo.data(), lo.size()))) return rc;
+    build_images(w_hh, w_ih, b_ih, b_hh, M_MIXED, hi, lo);
+    if ((rc = upload(h, &s->d_img_mhi, hi.data(), hi.size() * sizeof(__half)))) return rc;
+    if ((rc = upload(h, &s->d_img_mlo, lo.data(), lo.size()))) return rc;
     return RD_OK;
 }
 
@@ -748,8 +842,34 @@ extern "C" int rd_debug_prof(unsigned long long* out16) {
 void rd_tc_destroy(rd_handle* h) {
     if (!h->tc) return;
     cudaFree(h->tc->d_img_fast); cudaFree(h->tc->d_img_hi); cudaFree(h->tc->d_img_lo);
+    cudaFree(h->tc->d_img_mhi); cudaFree(h->tc->d_img_mlo);
     delete h->tc;
     h->tc = nullptr;
+}
+
+template <int MODE>
+static int launch_pair_kernel(rd_handle* h, bool* attr_set, const uint8_t* d_seq, const int64_t* d_off, int ostride,
+                              const uint32_t* splan, const int32_t* perm, int L, int nt, const int64_t* d_n_reads,
+                              const uint8_t* ihi, const uint8_t* ilo, float* d_logits, cudaStream_t st) {
+    using C = Cfg<MODE>;
+    if (!*attr_set) {
+        RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<MODE, G_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        *attr_set = true;
+    }
+    const int pairs = (nt + 1) / 2, max_pairs = h->sm_count / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    cfg.blockDim = dim3(tc_threads(G_EXACT));
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
+    RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<MODE, G_EXACT>, d_seq, d_off, ostride, splan, perm, L, nt, d_n_reads,
+                                  ihi, ilo, wout, bout, lut, d_logits));
+    return RD_OK;
 }
 
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int L, int precision,
@@ -761,39 +881,23 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
     rd_tc_state* s = h->tc;
     if (!s) { h->err = "tensor-core state missing"; return RD_ERR_UNSUPPORTED; }
     if (precision == RD_PREC_TC_FAST) {
-        using C = Cfg<false>;
+        using C = Cfg<M_FAST>;
         if (!s->attr_fast) {
-            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<false, G_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<M_FAST, G_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
             s->attr_fast = true;
         }
         int grid = (int)(n_tiles < h->sm_count ? n_tiles : h->sm_count);
-        lstm_tc_kernel<false, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
+        lstm_tc_kernel<M_FAST, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
             d_seq, d_off, ostride, d_splan, d_perm, L, (int)n_tiles, d_n_reads, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
             h->d_revlut, d_logits);
+    } else if (precision == RD_PREC_TC_MIXED) {
+        int rc = launch_pair_kernel<M_MIXED>(h, &s->attr_mixed, d_seq, d_off, ostride, d_splan, d_perm, L, (int)n_tiles, d_n_reads,
+                                             s->d_img_mhi, s->d_img_mlo, d_logits, st);
+        if (rc) return rc;
     } else {
-        using C = Cfg<true>;
-        if (!s->attr_exact) {
-            RD_CUDA(h, cudaFuncSetAttribute(lstm_tc_kernel<true, G_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-            s->attr_exact = true;
-        }
-        int pairs = (int)((n_tiles + 1) / 2);
-        int max_pairs = h->sm_count / 2;
-        int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(tc_threads(G_EXACT));
-        cfg.dynamicSmemBytes = C::SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        const uint32_t* splan = d_splan; const int32_t* perm = d_perm;
-        int nt = (int)n_tiles;
-        const uint8_t* ihi = s->d_img_hi; const uint8_t* ilo = s->d_img_lo;
-        const float* wout = h->d_wout; const float* bout = h->d_bout; const float* lut = h->d_revlut;
-        RD_CUDA(h, cudaLaunchKernelEx(&cfg, lstm_tc_kernel<true, G_EXACT>, d_seq, d_off, ostride, splan, perm, L, nt, d_n_reads, ihi, ilo, wout, bout, lut,
-                                      d_logits));
+        int rc = launch_pair_kernel<M_EXACT>(h, &s->attr_exact, d_seq, d_off, ostride, d_splan, d_perm, L, (int)n_tiles, d_n_reads,
+                                             s->d_img_hi, s->d_img_lo, d_logits, st);
+        if (rc) return rc;
     }
     h->launches += 1;
     RD_CUDA(h, cudaGetLastError());

@@ -9,7 +9,12 @@ Tolerances (stated once, used everywhere):
     is for reads of up to 100 steps and scales linearly with -l beyond that (rounding drift of a
     recurrence grows with its length: torch-CPU fp32 itself moves from 7e-6 at 100 bp to 3e-5 at
     300 bp against the fp64 restatement; tc_exact measures 1.5e-5 / 9e-5, tests/len_err_report.py)
+  * precision tc_mixed (fp16 main pass + e5m2 correction pass): |dlogit| <= 3e-3, |dp| <= 1e-3 (the tolerance
+    SURVEY.md 8c suggests for the exact mode), labels identical outside |margin| <= 6e-3; same length scaling
   * precision tc_fast: |dlogit| <= 5e-2, |dp| <= 2e-2, flip rate reported/asserted < 0.1 %
+  * precision tc_auto (tc_fast + tc_exact over the low-margin band): logits/probabilities to the tc_fast bounds,
+    LABELS to the tc_exact rule (identical outside |margin| <= 4e-4)
+Every parametrised test runs over the fixed list PRECISIONS: a mode that fails to launch fails the test.
 """
 import numpy as np
 import pytest
@@ -23,21 +28,16 @@ from ribodetector_b200.utils import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": (2e-4, 1e-4), "tc_exact": (2e-4, 1e-4), "tc_fast": (5e-2, 2e-2)}
+PRECISIONS = ["fp32", "tc_exact", "tc_mixed", "tc_fast", "tc_auto"]
+TOL = {"fp32": (2e-4, 1e-4), "tc_exact": (2e-4, 1e-4), "tc_mixed": (3e-3, 1e-3), "tc_fast": (5e-2, 2e-2),
+       "tc_auto": (5e-2, 2e-2)}
+# labels must equal the reference's for every read whose reference margin |l1 - l0| exceeds this
+BAND = {"fp32": 4e-4, "tc_exact": 4e-4, "tc_mixed": 6e-3, "tc_fast": 1e-1, "tc_auto": 4e-4}
 
 
-def built_precisions(model):
-    """Precision modes this library build supports (tensor-core modes land after fp32)."""
-    out = ["fp32"]
-    seq, off = encoders.flatten_reads(["ACGT" * 10] * 4)
-    for p in ("tc_exact", "tc_fast"):
-        try:
-            model.classify(seq, off, 40, precision=p)
-            torch.cuda.synchronize()
-            out.append(p)
-        except _lib.RdError:
-            pass
-    return out
+def built_precisions(model=None):
+    """Every precision mode of the library — a fixed list: a mode that is missing or fails raises in the caller."""
+    return list(PRECISIONS)
 
 
 def check_logits(got, ref, prec, max_len=100):
@@ -51,8 +51,8 @@ def check_logits(got, ref, prec, max_len=100):
     assert d <= tol_l, "max |dlogit| %.3e > %.1e (%s)" % (d, tol_l, prec)
     assert dp <= tol_p, "max |dp| %.3e > %.1e (%s)" % (dp, tol_p, prec)
     margin = np.abs(ref[:, 1] - ref[:, 0])
-    out_band = margin > 2 * tol_l
-    assert (got.argmax(1) == ref.argmax(1))[out_band].all()
+    out_band = margin > BAND[prec] * scale
+    assert (got.argmax(1) == ref.argmax(1))[out_band].all(), "label flip outside the %.1e band (%s)" % (BAND[prec] * scale, prec)
     return d
 
 
@@ -79,19 +79,20 @@ def test_onehot_ragged_truncates_and_scans_many_blocks(gpu_model):
 
 
 # ---- K2+K3 vs the reference's golden logits ----------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("case", ["se_L100", "se_L150", "se_L300"])
 @pytest.mark.parametrize("semantics", ["packed", "padded"])
-def test_logits_match_reference_golden(gpu_model, case, semantics):
+def test_logits_match_reference_golden(gpu_model, case, semantics, prec):
+    """model.py:32-37 / model_cpu.py:29-37 outputs written by the reference itself (oracle/gen_golden.py)."""
     g = load_golden(case)
     L = int(g["max_len"])
-    for prec in built_precisions(gpu_model):
-        logits, probs, labels = gpu_model.classify(g["seq"], g["off"], L, semantics=semantics,
-                                                   precision=prec, want_probs=True)
-        got = logits.cpu().numpy()
-        check_logits(got, g["logits_" + semantics], prec, L)
-        check_logits(got, g["logits_%s_f64" % semantics], prec, L)
-        assert np.array_equal(labels.cpu().numpy(), pairs.argmax_labels(got))
-        assert np.abs(probs.cpu().numpy() - softmax2(got.astype(np.float64))).max() < 1e-6
+    logits, probs, labels = gpu_model.classify(g["seq"], g["off"], L, semantics=semantics,
+                                               precision=prec, want_probs=True)
+    got = logits.cpu().numpy()
+    check_logits(got, g["logits_" + semantics], prec, L)
+    check_logits(got, g["logits_%s_f64" % semantics], prec, L)
+    assert np.array_equal(labels.cpu().numpy(), pairs.argmax_labels(got))
+    assert np.abs(probs.cpu().numpy() - softmax2(got.astype(np.float64))).max() < 1e-6
 
 
 def test_dropin_call_takes_reference_collate_outputs(gpu_model):
@@ -149,14 +150,43 @@ def test_ties_go_to_class0(gpu_model):
 
 
 # ---- seeded inputs vs the oracle ---------------------------------------------------------------------
+_RAGGED = {}
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("semantics", ["packed", "padded"])
-def test_ragged_reads_match_oracle(gpu_model, numpy_oracle, semantics):
+def test_ragged_reads_match_oracle(gpu_model, numpy_oracle, semantics, prec):
     seq, off = synth.synth_reads(3000, 1, 260, 11, n_frac=0.02)
-    reads = synth.to_strings(seq, off)
-    ref = numpy_oracle.logits(reads, 200, semantics)
-    for prec in built_precisions(gpu_model):
-        got = gpu_model.classify(seq, off, 200, semantics=semantics, precision=prec)[0].cpu().numpy()
-        check_logits(got, ref, prec, 200)
+    if semantics not in _RAGGED:
+        _RAGGED[semantics] = numpy_oracle.logits(synth.to_strings(seq, off), 200, semantics)
+    got = gpu_model.classify(seq, off, 200, semantics=semantics, precision=prec)[0].cpu().numpy()
+    check_logits(got, _RAGGED[semantics], prec, 200)
+
+
+def test_low_margin_and_rrna_enriched_reads_match_oracle(gpu_model, numpy_oracle):
+    """The reads that decide labels: out of 2^20 random 100 bp reads, the 3 000 with the smallest |margin| and 3 000
+    of the reads labelled rRNA (picked with the on-device fp32 kernel; the verdict comes from the fp64 oracle),
+    every precision against the oracle.  I.i.d. reads alone put only ~1 % of the set near the decision boundary."""
+    n = 1 << 20
+    seq, off = synth.synth_reads_fixed(n, 100, synth.SEED_BASE + 77)
+    sel = gpu_model.classify(seq, off, 100, precision="fp32")[0].cpu().numpy().astype(np.float64)
+    m = sel[:, 1] - sel[:, 0]
+    low = np.argsort(np.abs(m))[:3000]
+    pos = np.flatnonzero(m > 0)[:3000]
+    idx = np.unique(np.concatenate([low, pos]))
+    assert np.abs(m[low]).max() < 0.3 and len(pos) == 3000
+    s2 = seq.reshape(n, 100)[idx].reshape(-1)
+    o2 = np.arange(len(idx) + 1, dtype=np.int64) * 100
+    ref = numpy_oracle.logits(synth.to_strings(s2, o2), 100, "packed")
+    rm = np.abs(ref[:, 1] - ref[:, 0])
+    for prec in PRECISIONS:
+        got = gpu_model.classify(s2, o2, 100, precision=prec)[0].cpu().numpy().astype(np.float64)
+        d = check_logits(got, ref, prec)
+        flips = got.argmax(1) != ref.argmax(1)
+        print("%-8s enriched set (%d reads, %d with |margin| < 0.05): max|dlogit| %.2e, flips %d (all inside |margin| <= %.1e)"
+              % (prec, len(idx), int((rm < 0.05).sum()), d, int(flips.sum()), BAND[prec]))
+        if prec in ("fp32", "tc_exact", "tc_auto"):
+            assert flips.sum() <= 2
 
 
 def test_fixed_100bp_reads_match_torch_oracle(gpu_model, torch_oracle):
@@ -253,14 +283,17 @@ def test_tc_modes_match_fp32_kernel_on_one_million_reads(gpu_model):
         logits, _, labels = gpu_model.classify(seq, off, 100, precision=prec, counts=counts)
         got = logits.cpu().numpy().astype(np.float64)
         tol_l, _ = TOL[prec]
+        band = BAND[prec]
         d = np.abs(got - ref).max()
         flips = (got.argmax(1) != ref.argmax(1))
         print("%s: max|dlogit| vs fp32 kernel = %.3e, label flips = %d / %d (in-band reads: %d)"
-              % (prec, d, flips.sum(), n, (margin <= 2 * tol_l).sum()))
+              % (prec, d, flips.sum(), n, (margin <= band).sum()))
         assert d <= tol_l
-        assert not flips[margin > 2 * tol_l].any()
-        if prec == "tc_exact":
-            assert flips.sum() <= 10 and (margin <= 2 * tol_l).sum() < 1e-3 * n
+        assert not flips[margin > band].any()
+        if prec in ("tc_exact", "tc_auto"):
+            assert flips.sum() <= 10 and (margin <= band).sum() < 1e-3 * n
+        elif prec == "tc_mixed":
+            assert flips.sum() <= 100 and (margin <= band).sum() < 1e-2 * n
         else:
             assert flips.mean() < 1e-3
         lab = labels.cpu().numpy()
@@ -429,7 +462,8 @@ def test_bitwise_determinism_and_batch_independence(gpu_model):
         assert np.array_equal(a[:5000], c)
 
 
-def test_saturating_and_repetitive_reads(gpu_model, numpy_oracle):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_saturating_and_repetitive_reads(gpu_model, numpy_oracle, prec):
     """Homopolymers, short tandem repeats and all-N runs at 300 steps: gates sit in saturation for hundreds of
     steps (exercises the exponent clamps of the exact cell and the zero-row input)."""
     reads = []
@@ -441,10 +475,9 @@ def test_saturating_and_repetitive_reads(gpu_model, numpy_oracle):
     seq, off = encoders.flatten_reads(reads)
     for sem in ("packed", "padded"):
         ref = numpy_oracle.logits(reads, 300, sem)
-        for prec in built_precisions(gpu_model):
-            got = gpu_model.classify(seq, off, 300, semantics=sem, precision=prec)[0].cpu().numpy()
-            assert np.isfinite(got).all()
-            check_logits(got, ref, prec, 300)
+        got = gpu_model.classify(seq, off, 300, semantics=sem, precision=prec)[0].cpu().numpy()
+        assert np.isfinite(got).all()
+        check_logits(got, ref, prec, 300)
 
 
 def test_tc_auto_labels_equal_tc_exact(gpu_model):
