@@ -64,12 +64,21 @@ typedef struct rd_handle rd_handle;
  *              reads): LABELS equal TC_EXACT's, logits are exact-grade inside the band and fast-grade
  *              (|dlogit| <= 5e-2 * max(1, max_len/100)) outside it                                    */
 #define RD_PREC_TC_AUTO  3
-/*   TC_MIXED : the TC_EXACT structure with the two correction passes in tcgen05 kind::f8f6f4 (e5m2, K = 32 per
+/*   TC_MIXED_RAW : the TC_EXACT structure with the two correction passes in tcgen05 kind::f8f6f4 (e5m2, K = 32 per
  *              MMA): fp16 main pass + one 8-bit pass over [W_lo | W_hi] . [h_hi ; h_lo] = 17 MMAs per chunk
- *              instead of 25, same few-ulp ex2/rcp activations.  |dlogit| <= 2e-3 * max(1, max_len/100),
- *              |dprob| <= 1e-3 (SURVEY.md 8c's tolerance), labels identical outside |margin| <= 4e-3 * max(1, max_len/100) */
+ *              instead of 25, same few-ulp ex2/rcp activations.  With s = max(1, max_len/100):
+ *              |dlogit| <= 3e-3 * s^3, |dprob| <= 1e-3 * s^3 (SURVEY.md 8c's tolerance at 100 bp; measured over 2^20
+ *              reads per length: 1.7e-3 / 7.6e-4 at 100 bp, 7.0e-2 / 6.1e-3 at 300 bp, where the 3-pass mode itself
+ *              moves 1.6e-3 away from the fp32 CUDA-core kernel — profiles/r2_prec_err_big.txt)
+ *   TC_MIXED : two passes like TC_AUTO — TC_MIXED_RAW over every read, then TC_EXACT over the reads whose margin is
+ *              below RD_BAND_MIXED * s^2 (12x / 2.6x the largest margin error measured for the raw kernel at
+ *              100 / 300 bp; 0.15 % / 1.5 % of random reads): LABELS equal TC_EXACT's, logits exact-grade inside the
+ *              band and to the TC_MIXED_RAW tolerance outside it.  The default of the command line and of bench.py. */
 #define RD_PREC_TC_MIXED 4
-#define RD_PREC_LAST     RD_PREC_TC_MIXED
+#define RD_PREC_TC_MIXED_RAW 5
+#define RD_BAND_FAST  0.25f
+#define RD_BAND_MIXED 0.04f
+#define RD_PREC_LAST     RD_PREC_TC_MIXED_RAW
 
 /* paired-end combination, detect.py:616-663 (`-e/--ensure`) */
 #define RD_PAIR_NONE   0   /* argmax(logits_r1 + logits_r2)            detect.py:655-661 */

@@ -21,9 +21,9 @@ _STATE = {}
 
 
 def _init(weights):
+    os.environ["OMP_NUM_THREADS"] = "1"
     import torch
     torch.set_num_threads(1)
-    os.environ["OMP_NUM_THREADS"] = "1"
     from .model_torch import TorchOracle
     _STATE["oracle"] = TorchOracle(weights)
 
@@ -33,13 +33,12 @@ def _work(args):
     b = seq.tobytes()
     base = int(off[0])
     reads = [b[int(off[i]) - base:int(off[i + 1]) - base] for i in range(len(off) - 1)]
-    logits = _STATE["oracle"].logits_padded(reads, max_len, batch=BATCH)
-    return np.argmax(logits, axis=1).astype(np.int8)
+    return _STATE["oracle"].logits_padded(reads, max_len, batch=BATCH)
 
 
 def classify(seq, off, max_len, weights, threads=None):
-    """→ (labels int8[n], seconds).  Batches of 1024 reads fanned out over `threads` forked
-    single-threaded workers, like detect_cpu.py:283-298."""
+    """→ (labels int8[n], logits float32[n,2], seconds).  Batches of 1024 reads fanned out over `threads` forked
+    single-threaded workers, like detect_cpu.py:283-298; argmax as in detect_cpu.py:705."""
     threads = threads or os.cpu_count() or 1
     n = len(off) - 1
     jobs = []
@@ -52,5 +51,5 @@ def classify(seq, off, max_len, weights, threads=None):
         t0 = time.perf_counter()
         parts = pool.map(_work, jobs, chunksize=1)
         dt = time.perf_counter() - t0
-    labels = np.concatenate(parts) if parts else np.zeros(0, np.int8)
-    return labels, dt
+    logits = np.concatenate(parts) if parts else np.zeros((0, 2), np.float32)
+    return np.argmax(logits, axis=1).astype(np.int8), logits, dt

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RD_B200_LIB") or os.path.join(_HERE, "librd_b200.so")
 RD_OK, RD_ERR_INVALID, RD_ERR_CUDA, RD_ERR_EMPTY_READ, RD_ERR_NOMEM, RD_ERR_UNSUPPORTED, RD_ERR_PARSE = range(7)
 FMT = {"fastq": 0, "fasta": 1}
 SEM = {"packed": 0, "padded": 1}
-PREC = {"fp32": 0, "tc_exact": 1, "tc_fast": 2, "tc_auto": 3, "tc_mixed": 4}
+PREC = {"fp32": 0, "tc_exact": 1, "tc_fast": 2, "tc_auto": 3, "tc_mixed": 4, "tc_mixed_raw": 5}
 PAIR = {"none": 0, "rrna": 1, "norrna": 2, "both": 3}
 ONEHOT = {"ragged": 0, "padded": 1}
 RD_MAX_LEN = 4096

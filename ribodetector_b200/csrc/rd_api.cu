@@ -248,11 +248,18 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
     {
         StageTimer tm(h, 1, st);
         if (precision == RD_PREC_FP32) rc = rd_launch_lstm_simt(h, tiles, max_len, d_logits, st);
-        else if (precision == RD_PREC_TC_AUTO) {
-            // fast pass over everything, exact pass over the low-margin reads (their count stays on the device)
+        else if (precision == RD_PREC_TC_AUTO || precision == RD_PREC_TC_MIXED) {
+            // two passes: the cheaper kernel over everything, then the exact kernel over the reads whose margin from the
+            // first pass is inside a band several times the first pass's error bound (their slots are compacted on the
+            // device and their count stays there, so nothing synchronises with the host): LABELS equal TC_EXACT's
+            const bool fast = precision == RD_PREC_TC_AUTO;
+            // (the error of a recurrence grows with its length: linearly for the fast mode's bound, and the largest margin
+            //  error of the mixed kernel over 2^20 reads per length grows like the square: profiles/r2_prec_err_big.txt)
+            const float len_scale = max_len > 100 ? (float)max_len / 100.0f : 1.0f;
+            const float tau = fast ? RD_BAND_FAST * len_scale : RD_BAND_MIXED * len_scale * len_scale;
             rc = ensure_band(h);
-            if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_FAST, d_logits, st, nullptr, nullptr, nullptr, ostride);
-            const float tau = 0.25f * (max_len > 100 ? (float)max_len / 100.0f : 1.0f);
+            if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, fast ? RD_PREC_TC_FAST : RD_PREC_TC_MIXED_RAW, d_logits, st,
+                                            nullptr, nullptr, nullptr, ostride);
             if (!rc) rc = rd_launch_band_select(h, d_logits, tiles, tau, st);
             const int64_t nb = (tiles * RD_TILE + 255) / 256;
             if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, RD_PREC_TC_EXACT, d_logits, st, h->d_splan2,

@@ -49,6 +49,9 @@ __device__ unsigned long long g_tc_prof[16];
 #ifndef RD_TC_EXACT_EARLY_MAIN
 #define RD_TC_EXACT_EARLY_MAIN 1
 #endif
+#ifndef RD_TC_DEFER_PUBLISH
+#define RD_TC_DEFER_PUBLISH 1
+#endif
 #ifndef RD_TC_G_FAST
 #define RD_TC_G_FAST 4
 #endif
@@ -146,6 +149,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// the same, pinned behind the computation of `dep` (an unused operand: keeps ptxas from hoisting the wait above the
+// arithmetic that is meant to cover the store latency)
+__device__ __forceinline__ void tc_wait_st_after(uint32_t dep) {
+    asm volatile("tcgen05.wait::st.sync.aligned; // %0" ::"r"(dep) : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -164,6 +172,18 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
                  "r"(d) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(a) : "memory");
+}
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
 }
@@ -321,8 +341,8 @@ __device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo
         const float P = fmaf(A, B1, B1);                          // (1+A)(1+B)
         const float Q = 1.0f + F;
         const float num = fmaf(c_old, P, fmaf(-B, Q, Q));         // c (1+A)(1+B) + (1-B)(1+F)
-        c_new = num * rcp_mufu(Q * P);
-        const float O = ex2_mufu(fminf(zo, EXACT_CLAMP));
+        c_new = num * (RD_TC_EXACT_FMA_RCP >= 2 ? rcp_fma(Q * P) : rcp_mufu(Q * P));
+        const float O = ex2_mufu(zo);                             // unclamped: O = inf gives den = inf, 1/den = 0, h = 0 (D is finite)
         const float D = ex2_mufu(fminf(EXACT_SCALE_G * c_new, EXACT_CLAMP));
         const float D1 = 1.0f + D;
         const float den = fmaf(O, D1, D1);                        // (1+O)(1+D)
@@ -378,7 +398,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
     constexpr bool EXACT = C::EXACT;                  // split precision on a CTA pair (M_EXACT and M_MIXED)
     constexpr int CG = C::CG;
     constexpr int EPI_WARPS = epi_warps(G), EPI_THREADS = EPI_WARPS * 32, TC_THREADS = tc_threads(G);
-    constexpr int SUBS = 16 / G;                      // 8-unit groups per warp per step
+    static_assert(G == 4, "the activation warps are laid out as 4 lane quarters x 4 unit groups");
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_hi = s_base, s_lo = s_base + C::OFF_LO, s_x = s_base + C::OFF_X;
@@ -399,7 +419,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_tile, EPI_WARPS * CG);
-        for (int i = 0; i < KCHUNKS; ++i) mbar_init(bar_h + 8 * i, 8 * CG);      // 2 groups x 4 quarters publish a K-chunk
+        for (int i = 0; i < KCHUNKS; ++i) mbar_init(bar_h + 8 * i, EPI_WARPS * CG);   // every activation warp publishes 4 units of each K-chunk
         for (int i = 0; i < NBUF; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, EPI_WARPS * CG);
@@ -588,11 +608,11 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
             const int my_len = (int)(my_l64 < (int64_t)L ? my_l64 : (int64_t)L);
             const uint8_t* cptr = seq + my_b;
             auto code_at = [&](int t) -> uint32_t { return t < my_len ? rd_base_code(__ldg(cptr + t)) : 4u; };
-            float c[SUBS][8];
+            float c[MMA_CHUNKS][2][4];                                   // cell states: [MMA chunk][half][unit]
 #pragma unroll
-            for (int g = 0; g < SUBS; ++g)
+            for (int g = 0; g < MMA_CHUNKS; ++g)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) c[g][u] = 0.f;
+                for (int u = 0; u < 4; ++u) { c[g][0][u] = 0.f; c[g][1][u] = 0.f; }
             float p0 = 0.f, p1 = 0.f;
             uint32_t code_next = 4u, code_next2 = 4u;
             if (par == 0) {
@@ -607,95 +627,103 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
 
             for (int t = 0; t < T; ++t) {
                 if (par == 0) code_next2 = code_at(t + 2);
-                const bool active = t < nf;
                 const bool last = t == nf - 1;
+                const bool any_last = __any_sync(0xffffffffu, last);       // warp-uniform: the FC is skipped on most steps
                 const bool more = t + 1 < T;
                 const uint32_t wr = (uint32_t)(t & 1);                                   // h_t, x_{t+1} go to buffer t&1
                 const uint32_t awr = tmem + wr * C::ACOLS + lane_off;
+                // One half-chunk = this thread's i,f,g,o of 4 hidden units (16 accumulator columns).  Across the four
+                // unit-group warps of a lane quarter a half-chunk is 16 hidden units = one K-chunk of the next step.
+                auto half_step = [&](const uint32_t (&v)[16], const int mc, const int half) {
+                    const int u0 = 32 * mc + 16 * half + 4 * par;        // first of the 4 hidden units
+                    float hv[4];
 #pragma unroll
-                for (int cc = 0; cc < SUBS; ++cc) {
-                    // this warp's cc-th group of the step: j = cc*G + g; MMA chunk mc = j/4, K-chunk kc = j/2
-                    const int mc = (cc * G) >> 2, buf = mc & 1;
-                    const int j = cc * G + par;
-                    const bool first_of_chunk = G == 4 || (cc & 1) == 0, last_of_chunk = G == 4 || (cc & 1) == 1;
-                    { PROF_T0();
-                    if (first_of_chunk) mbar_wait(bar_full + 8 * buf, (mc >> 1) & 1);
-                    PROF_ADD(pe_full);
-#ifdef RD_TC_PROFILE
-                    if (mc == 0) pe_full0 += clock64() - _p0;
-#endif
-                    }
-                    tc_fence_after();
-                    uint32_t v[32];
-                    { PROF_T0();
-                    tmem_ld32(tmem + (uint32_t)(C::DCOL0 + buf * MMA_N + (j & 3) * 32) + lane_off, v);
-                    tc_wait_ld();
-                    PROF_ADD(pe_ld); }
-                    if (last_of_chunk) {                                 // this warp has drained its part of the D buffer
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_empty + 8 * buf, 0); else mbar_arrive(bar_empty + 8 * buf); }
-                    }
-
-                    float hv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         float cn;
-                        lstm_cell<MODE>(__uint_as_float(v[u]), __uint_as_float(v[8 + u]), __uint_as_float(v[16 + u]),
-                                         __uint_as_float(v[24 + u]), c[cc][u], cn, hv[u]);
-                        if (active) c[cc][u] = cn;
+                        lstm_cell<MODE>(__uint_as_float(v[u]), __uint_as_float(v[4 + u]), __uint_as_float(v[8 + u]),
+                                        __uint_as_float(v[12 + u]), c[mc][half][u], cn, hv[u]);
+                        c[mc][half][u] = cn;     // (a read that has finished keeps stepping on zero rows: nothing reads its state)
                     }
-                    if (last) {        // fused FC: this thread's 8 units of W_out[:, :H] . h_fwd   (model.py:36)
-                        const int u0 = j * 8;
+                    if (any_last && last) {        // fused FC: this thread's units of W_out[:, :H] . h_fwd   (model.py:36)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
+                        for (int u = 0; u < 4; ++u) {
                             p0 = fmaf(wout_s[u0 + u], hv[u], p0);
                             p1 = fmaf(wout_s[RD_H + u0 + u], hv[u], p1);
                         }
                     }
                     if (more) {
-                        const uint32_t hcol = awr + (uint32_t)(4 * j);
+                        const uint32_t hcol = awr + (uint32_t)(u0 >> 1);
+                        __half2 ha = __floats2half2_rn(hv[0], hv[1]), hb = __floats2half2_rn(hv[2], hv[3]);
+                        const uint32_t hia = *reinterpret_cast<uint32_t*>(&ha), hib = *reinterpret_cast<uint32_t*>(&hb);
+                        // K-chunk kc of h_t is published (h_ready[kc]) once every store of it has landed in tensor memory.
+                        // The publish of the PREVIOUS half-chunk sits here, behind this half-chunk's cells, so that
+                        // tcgen05.wait::st finds its stores long complete instead of stalling the warp ~100 cycles eight
+                        // times a step; only the step's last half-chunk is published right after its own stores.
+                        auto publish = [&](const int kc, const uint32_t dep) {
+                            PROF_T0();
+                            if (RD_TC_DEFER_PUBLISH) tc_wait_st_after(dep); else tc_wait_st();
+                            tc_fence_before();
+                            __syncwarp();
+                            const uint32_t hb_bar = bar_h + 8 * (uint32_t)kc;
+                            if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(hb_bar, 0); else mbar_arrive(hb_bar); }
+                            PROF_ADD(pe_st);
+                        };
+                        const int kc = 2 * mc + half;
+                        if (RD_TC_DEFER_PUBLISH && kc > 0) publish(kc - 1, hia);
                         if constexpr (MODE == M_MIXED) {
-                            // fp16(h'), its top byte pattern as e5m2 (h_hi8), and the residual h' - fp16(h') as e5m2 (h_lo8)
-                            uint32_t hi[4], hi8[4], lo8[4];
-#pragma unroll
-                            for (int p2 = 0; p2 < 4; ++p2) {
-                                __half2 h2 = __floats2half2_rn(hv[2 * p2], hv[2 * p2 + 1]);
-                                float2 back = __half22float2(h2);
-                                hi[p2] = *reinterpret_cast<uint32_t*>(&h2);
-                                hi8[p2] = e5m2x2_from_h2(hi[p2]);
-                                lo8[p2] = e5m2x2_from_f32((hv[2 * p2] - back.x) * MIXED_LS, (hv[2 * p2 + 1] - back.y) * MIXED_LS);
-                            }
-                            tmem_st4(hcol, hi[0], hi[1], hi[2], hi[3]);
-                            tmem_st2(awr + (uint32_t)(64 + 2 * j), hi8[0] | (hi8[1] << 16), hi8[2] | (hi8[3] << 16));
-                            tmem_st2(awr + (uint32_t)(96 + 2 * j), lo8[0] | (lo8[1] << 16), lo8[2] | (lo8[3] << 16));
+                            // fp16(h'), its top byte as e5m2 (h_hi8), and the residual h' - fp16(h') as e5m2 (h_lo8)
+                            const float2 ba = __half22float2(ha), bb = __half22float2(hb);
+                            const uint32_t hi8 = e5m2x2_from_h2(hia) | (e5m2x2_from_h2(hib) << 16);
+                            const uint32_t lo8 = e5m2x2_from_f32((hv[0] - ba.x) * MIXED_LS, (hv[1] - ba.y) * MIXED_LS) |
+                                                 (e5m2x2_from_f32((hv[2] - bb.x) * MIXED_LS, (hv[3] - bb.y) * MIXED_LS) << 16);
+                            tmem_st2(hcol, hia, hib);
+                            tmem_st1(awr + (uint32_t)(64 + (u0 >> 2)), hi8);
+                            tmem_st1(awr + (uint32_t)(96 + (u0 >> 2)), lo8);
                         } else if constexpr (EXACT) {
-                            uint32_t hi[4], lo[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                __half2 h2 = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
-                                float2 back = __half22float2(h2);
-                                hi[j] = *reinterpret_cast<uint32_t*>(&h2);
-                                lo[j] = pack_h2(hv[2 * j] - back.x, hv[2 * j + 1] - back.y);
-                            }
-                            tmem_st4(hcol, hi[0], hi[1], hi[2], hi[3]);
-                            tmem_st4(hcol + 64, lo[0], lo[1], lo[2], lo[3]);
+                            const float2 ba = __half22float2(ha), bb = __half22float2(hb);
+                            tmem_st2(hcol, hia, hib);
+                            tmem_st2(hcol + 64, pack_h2(hv[0] - ba.x, hv[1] - ba.y), pack_h2(hv[2] - bb.x, hv[3] - bb.y));
                         } else {
-                            tmem_st4(hcol, pack_h2(hv[0], hv[1]), pack_h2(hv[2], hv[3]), pack_h2(hv[4], hv[5]),
-                                     pack_h2(hv[6], hv[7]));
+                            tmem_st2(hcol, hia, hib);
                         }
-                        if (cc == 0 && par == 0) {                        // x_{t+1} rides with K-chunk 0
+                        if (mc == 0 && half == 0 && par == 0) {           // x_{t+1} rides with K-chunk 0
                             st_x_row(x_row + wr * X_BYTES, code_next);
                             fence_async_smem();
                         }
-                        { PROF_T0();
-                        tc_wait_st();
-                        tc_fence_before();
-                        __syncwarp();
-                        const uint32_t hb = bar_h + 8 * (uint32_t)(j >> 1);
-                        if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(hb, 0); else mbar_arrive(hb); }
-                        PROF_ADD(pe_st); }
+                        if (!RD_TC_DEFER_PUBLISH || kc == KCHUNKS - 1) publish(kc, hia);
                     }
+                };
+                // Software pipeline over the step's 8 half-chunks: the tcgen05.ld of the next half-chunk is in flight
+                // while the cells of the current one run on the XU/FMA pipes (two 16-register buffers).
+                uint32_t va[16], vb[16];
+                const uint32_t dthr = tmem + (uint32_t)(C::DCOL0 + par * 32) + lane_off;   // this thread's columns of D buffer 0
+                { PROF_T0();
+                mbar_wait(bar_full, 0);
+                PROF_ADD(pe_full);
+#ifdef RD_TC_PROFILE
+                pe_full0 += clock64() - _p0;
+#endif
+                }
+                tc_fence_after();
+                tmem_ld16(dthr, va);
+#pragma unroll
+                for (int mc = 0; mc < MMA_CHUNKS; ++mc) {
+                    const int buf = mc & 1;
+                    { PROF_T0(); tc_wait_ld(); PROF_ADD(pe_ld); }
+                    tmem_ld16(dthr + (uint32_t)(buf * MMA_N + 16), vb);
+                    half_step(va, mc, 0);
+                    { PROF_T0(); tc_wait_ld(); PROF_ADD(pe_ld); }
+                    tc_fence_before();                                   // this warp has drained its part of the D buffer
+                    __syncwarp();
+                    if (lane == 0) { if (CG == 2 && rank != 0) mbar_arrive_remote(bar_empty + 8 * buf, 0); else mbar_arrive(bar_empty + 8 * buf); }
+                    if (mc + 1 < MMA_CHUNKS) {
+                        { PROF_T0();
+                        mbar_wait(bar_full + 8 * ((mc + 1) & 1), ((mc + 1) >> 1) & 1);
+                        PROF_ADD(pe_full); }
+                        tc_fence_after();
+                        tmem_ld16(dthr + (uint32_t)(((mc + 1) & 1) * MMA_N), va);
+                    }
+                    half_step(vb, mc, 1);
                 }
                 code_next = code_next2;
             }
@@ -738,8 +766,13 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
 }
 
 // ---- host side: weight images ----------------------------------------------------------------------
-// D column n  <->  hidden unit / gate:  n = 32*j + 8*gate + u8  with unit = 8*j + u8, gate in (i,f,g,o)
-inline int col_to_row(int n) { return ((n % 32) / 8) * RD_H + (n / 32) * 8 + (n % 8); }
+// D column n  <->  hidden unit / gate:  n = 128*mc + 32*par + 16*half + 4*gate + u4  (MMA chunk mc, activation-warp
+// unit group par, half-chunk, gate in (i,f,g,o)) holds  unit = 32*mc + 16*half + 4*par + u4: one tcgen05.ld.x16 hands a
+// thread i,f,g,o of 4 units, and the four unit groups of a half-chunk together own one 16-unit K-chunk of h.
+inline int col_to_row(int n) {
+    const int mc = n / 128, r = n % 128, par = r / 32, half = (r % 32) / 16, gate = (r % 16) / 4, u4 = r % 4;
+    return gate * RD_H + 32 * mc + 16 * half + 4 * par + u4;
+}
 
 // image[rank][kg][n_local][8] halfs; MMA chunk cc takes rows cc*NB .. cc*NB+NB-1 of each rank,
 // which are D columns cc*128 + rank*NB + i  (cta_group::2: each CTA supplies half of the N columns).
@@ -890,7 +923,7 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
         lstm_tc_kernel<M_FAST, G_FAST><<<grid, tc_threads(G_FAST), C::SMEM_BYTES, st>>>(
             d_seq, d_off, ostride, d_splan, d_perm, L, (int)n_tiles, d_n_reads, s->d_img_fast, nullptr, h->d_wout, h->d_bout,
             h->d_revlut, d_logits);
-    } else if (precision == RD_PREC_TC_MIXED) {
+    } else if (precision == RD_PREC_TC_MIXED || precision == RD_PREC_TC_MIXED_RAW) {
         int rc = launch_pair_kernel<M_MIXED>(h, &s->attr_mixed, d_seq, d_off, ostride, d_splan, d_perm, L, (int)n_tiles, d_n_reads,
                                              s->d_img_mhi, s->d_img_mlo, d_logits, st);
         if (rc) return rc;

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from .fastx import _host_array, get_seq_format, open_text
+from .fastx import _host_array, get_seq_format, open_text, warn_if_truncated
 
 
 class _Unit:
@@ -190,8 +190,14 @@ class FastqGpuStream:
                         raise RuntimeError("a FASTQ record does not fit the %d-byte block" % self.block_bytes)
                 if final and (n == 0 or not any(t.size for t in tails)):
                     # (a capped block leaves whole records behind: they go round again; a truncated last record is dropped)
-                    if ends == 2 and any(int((t == 10).sum()) >= 4 for t in tails):
+                    # one end holding a further COMPLETE record (four lines; the last one may lack its newline) means the
+                    # files differ in length, as the host path (_pair_chunks) reports
+                    def lines(t):
+                        return int((t == 10).sum()) + int(t.size > 0 and t[-1] != 10)
+                    if ends == 2 and any(lines(t) >= 4 for t in tails):
                         raise RuntimeError("The two input files hold different numbers of reads.")
+                    for t in tails:
+                        warn_if_truncated(t, int(self.counts.sum()))
                     break
         finally:
             inflight.put(None)

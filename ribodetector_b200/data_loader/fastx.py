@@ -281,6 +281,16 @@ class RecordChunk:
         return out
 
 
+def warn_if_truncated(tail, records_read):
+    """The reference's parser silently drops an unfinished final record (fastx_parser.py:15-47, PROBE in SURVEY.md
+    Appendix A); so does this reader, but it says so when the dropped bytes are more than white space."""
+    t = np.asarray(tail)
+    if t.size and (t > 0x20).any():
+        import warnings
+        warnings.warn("input ends inside a record: %d trailing bytes after record %d were dropped (truncated file?)"
+                      % (t.size, records_read), RuntimeWarning, stacklevel=3)
+
+
 class FastxReader:
     """Iterate RecordChunks of up to ``max_records`` records over a (optionally gzipped) FASTQ/FASTA
     file, holding one block of at most ``block_bytes`` of text at a time (bounded memory: the
@@ -301,15 +311,21 @@ class FastxReader:
         self.eof = False
         self.lib = _lib.load_library()
         self.records_read = 0
+        self.bytes_scanned = 0
+        self.rec_bytes = 512.0                 # running mean of the text bytes per record (first guess)
+        self.peak_buffer_bytes = 0
         self.wait_seconds = 0.0
         # buffer sets are recycled (RecordChunk.release): fresh 256 MB allocations per chunk cost more in
         # page faults than the scan itself
         self.free = queue.Queue()
 
     def close(self):
-        self.fh.close()
+        if self.fh is not None:
+            self.fh.close()
+            self.fh = None
         if self.pool is not None:
             self.pool.shutdown()
+            self.pool = None
 
     def _fill_parallel(self, buf, start):
         """Plain files: positional reads of the block's slices on a few threads (page-cache copies scale
@@ -363,21 +379,29 @@ class FastxReader:
         while True:
             if self.eof and self.tail.size == 0:
                 raise StopIteration
-            size = max(self.block_bytes, 2 * self.tail.size)
             cap = self.max_records
+            # Read only what `cap` records are expected to need (running mean of the record size, 25 % head room):
+            # the bytes carried over to the next call then stay a fraction of a chunk, so the carry copy is linear
+            # in the file size and the buffers never exceed block_bytes (a single record larger than the block
+            # still grows it).  An underestimate costs one rescan with a doubled estimate.
+            want = int(cap * self.rec_bytes * 1.25) + (1 << 16)
+            size = min(self.block_bytes, max(want, self.tail.size + (1 << 16)))
+            size = max(size, self.tail.size)
             try:
                 bs = self.free.get_nowait()                   # a recycled set (RecordChunk.release), else a fresh one:
             except queue.Empty:                               # callers that never release just allocate per chunk
                 bs = {}
             if bs.get("size", 0) < size or bs.get("cap", 0) < cap:
+                alloc = max(size, bs.get("size", 0))
                 bs.clear()
-                bs.update(size=size, cap=cap, buf=np.empty(size, np.uint8), seq=_host_array(size + 1, np.uint8, self.pinned),
+                bs.update(size=alloc, cap=cap, buf=np.empty(alloc, np.uint8), seq=_host_array(alloc + 1, np.uint8, self.pinned),
                           hdr=np.empty(2 * cap, np.int64), seq_off=_host_array(cap + 1, np.int64, self.pinned),
                           plus=np.empty(2 * cap, np.int64) if self.format == "fastq" else None,
                           qual=np.empty(2 * cap, np.int64) if self.format == "fastq" else None)
             buf, seq, hdr, plus, qual, seq_off = bs["buf"], bs["seq"], bs["hdr"], bs["plus"], bs["qual"], bs["seq_off"]
             buf[:self.tail.size] = self.tail
             fill = self._fill(buf[:size], self.tail.size) if not self.eof else self.tail.size
+            self.peak_buffer_bytes = max(self.peak_buffer_bytes, int(bs["size"]))
             consumed = ctypes.c_int64(0)
             n = self.lib.rd_scan_fastx(_p(buf), fill, _lib.FMT[self.format], int(self.eof), cap, _p(hdr), _p(plus),
                                        _p(qual), _p(seq), fill, _p(seq_off), ctypes.byref(consumed), self.threads)
@@ -386,19 +410,34 @@ class FastxReader:
                 msg = self.lib.rd_fastx_last_error().decode("utf-8", "replace")
                 raise ValueError("%s (record %d of the file)" % (msg, self.records_read))
             c = consumed.value
+            if n < cap and not self.eof and size < self.block_bytes:
+                # the estimate was too small for `cap` records: keep everything, read more, scan again
+                self.tail = buf[:fill].copy()
+                self.rec_bytes = max(2.0 * self.rec_bytes, (c / n) if n else 0.0)
+                self.free.put(bs)
+                continue
             self.tail = buf[c:fill].copy()
             if n == 0:
                 self.free.put(bs)
                 if self.eof:
+                    warn_if_truncated(self.tail, self.records_read)
                     self.tail = np.zeros(0, np.uint8)      # truncated final record: dropped like the reference
                     raise StopIteration
                 if c == 0:
                     self.block_bytes *= 2                    # one record larger than the block: grow and retry
                 continue
             self.records_read += n
+            self.bytes_scanned += c
+            self.rec_bytes = max(16.0, self.bytes_scanned / self.records_read)
             return RecordChunk(self.format, buf, int(n), hdr[:2 * n], None if plus is None else plus[:2 * n],
                                None if qual is None else qual[:2 * n], seq, seq_off[:n + 1],
                                on_release=lambda bs=bs: self.free.put(bs))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def partition_records(chunk, labels, want=(True, True, True), threads=4, scratch=None):

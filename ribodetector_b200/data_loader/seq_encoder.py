@@ -63,16 +63,18 @@ def load_reads(seq_file, label=None, max_len=100):
     if label is not None:
         raise NotImplementedError("labelled loading is a training helper of the reference (out of scope)")
     out = []
-    for chunk in FastxReader(seq_file):
-        out.extend(chunk.records())
-        chunk.release()
+    with FastxReader(seq_file) as reader:
+        for chunk in reader:
+            out.extend(chunk.records())
+            chunk.release()
     return out
 
 
 def _records(seq_file):
-    for chunk in FastxReader(seq_file, max_records=1 << 18):
-        yield from chunk.records()
-        chunk.release()
+    with FastxReader(seq_file, max_records=1 << 18) as reader:      # closed at StopIteration and when abandoned
+        for chunk in reader:
+            yield from chunk.records()
+            chunk.release()
 
 
 def get_seq_chunks(seq_file, chunk_size=1048576):

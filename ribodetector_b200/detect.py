@@ -387,8 +387,8 @@ none: give label based on the mean probability of read pair.
                       help='Use this parameter when having low memory. Parsing the file in chunks.\n'
                            'chunk = batch_size x chunk_size reads; without it chunks of 1 Mi reads are streamed.')
     args.add_argument('--log', default=None, type=str, help='Log file name')
-    args.add_argument('--precision', default='tc_exact', choices=['tc_exact', 'tc_mixed', 'tc_auto', 'tc_fast', 'fp32'],
-                      help='(extension) arithmetic of the recurrent contraction: tc_exact = tcgen05 3-pass fp16 split,\nfp32-grade logits (default); tc_fast = one fp16 pass; fp32 = CUDA cores')
+    args.add_argument('--precision', default='tc_mixed', choices=['tc_mixed', 'tc_exact', 'tc_auto', 'tc_fast', 'tc_mixed_raw', 'fp32'],
+                      help='(extension) arithmetic of the recurrent contraction: tc_mixed = tcgen05 fp16 pass + 8-bit correction pass,\nlow-margin reads re-run in tc_exact (default; labels = tc_exact); tc_exact = 3-pass fp16 split, fp32-grade logits;\ntc_auto = tc_fast + tc_exact on low-margin reads; tc_fast = one fp16 pass; fp32 = CUDA cores')
     args.add_argument('--host_ingest', action='store_true',
                       help='(extension) scan FASTQ records and partition the output on the host instead of the GPU\n'
                            '(FASTA inputs and --chunk_size runs always do)')

@@ -57,7 +57,7 @@ class SeqModel:
     """BiLSTM(4→128) + Linear(256→2) classifier.  ``model(x)`` returns raw logits ``[B, 2]``."""
 
     def __init__(self, input_size=4, hidden_size=128, num_layers=1, num_classes=2,
-                 batch_first=True, bidirectional=True, pack_seq=True, precision="tc_exact"):
+                 batch_first=True, bidirectional=True, pack_seq=True, precision="tc_mixed"):
         if (input_size, num_layers, num_classes, batch_first, bidirectional) != (4, 1, 2, True, True):
             raise ValueError("SeqModel kernels implement input_size=4, num_layers=1, num_classes=2, "
                              "batch_first=True, bidirectional=True (the shipped architecture)")
@@ -72,6 +72,7 @@ class SeqModel:
         self._weights = None
         self._handle = None
         self._device = None
+        self._alphabet = None
         self._lib = _lib.load_library()          # raises if the extension is missing
 
     # ---- nn.Module-like surface used by the reference loop -----------------------------------
@@ -388,7 +389,6 @@ class SeqModel:
         return np.array(list(sizes), np.int64).reshape(2, 3), np.array(list(counts), np.int64)
 
     # ---- drop-in __call__: the tensors the reference's collate functions produce -----------------
-    _ALPHABET = None
 
     def __call__(self, x):
         """x: a ReadBatch (this package's collate output), a PackedSequence of one-hot rows (detect.py:685) → packed semantics, or a padded
@@ -408,11 +408,11 @@ class SeqModel:
         else:
             raise TypeError("SeqModel expects a PackedSequence or a [B,T,4] tensor")
         B, T = padded.shape[0], padded.shape[1]
-        if SeqModel._ALPHABET is None or SeqModel._ALPHABET.device != self._device:
-            SeqModel._ALPHABET = torch.tensor(list(b"ACGTN"), dtype=torch.uint8, device=self._device)
+        if self._alphabet is None or self._alphabet.device != self._device:       # per instance: one model per GPU/thread
+            self._alphabet = torch.tensor(list(b"ACGTN"), dtype=torch.uint8, device=self._device)
         code = torch.where(padded.sum(2) == 0, torch.full((), 4, device=self._device),
                            padded.argmax(2))
-        bytes_bt = SeqModel._ALPHABET[code]
+        bytes_bt = self._alphabet[code]
         lens_d = lens.to(self._device)
         mask = torch.arange(T, device=self._device)[None, :] < lens_d[:, None]
         seq = bytes_bt[mask].contiguous()

@@ -18,6 +18,34 @@ def synth_reads_fixed(n, length, seed, n_frac=0.001):
     return seq, off
 
 
+_LUT4 = None
+
+
+def _fill_block(args):
+    out, seed, i, s, e, n_frac = args
+    global _LUT4
+    if _LUT4 is None:            # byte -> the four bases its 2-bit fields select, packed little-endian
+        r = np.arange(256, dtype=np.uint32)
+        _LUT4 = sum(_ALPHA[(r >> (2 * k)) & 3].astype(np.uint32) << (8 * k) for k in range(4)).astype(np.uint32)
+    rng = np.random.Generator(np.random.PCG64([seed, i]))
+    m = e - s
+    raw = np.frombuffer(rng.bytes((m + 3) // 4), dtype=np.uint8)
+    out[s:e] = _LUT4[raw].view(np.uint8)[:m]
+    if n_frac > 0:
+        k = rng.binomial(m, n_frac)
+        out[s + rng.integers(0, m, size=k)] = ord("N")
+
+
+def fill_bases(out, seed, n_frac=0.001, block=1 << 26, threads=8):
+    """Fill a uint8 array with i.i.d. ACGT (+ n_frac 'N'), 64-MB block by block from (seed, block index): the
+    generator for buffers of several GB (a quarter byte of randomness per base, blocks on a thread pool)."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = [(out, seed, i, s, min(out.size, s + block), n_frac) for i, s in enumerate(range(0, out.size, block))]
+    with ThreadPoolExecutor(max(1, min(threads, len(jobs)))) as ex:
+        list(ex.map(_fill_block, jobs))
+    return out
+
+
 def synth_reads(n, min_len, max_len, seed, n_frac=0.001):
     """n reads with length ~ U{min_len..max_len} → (uint8 bytes, int64 offsets [n+1])."""
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -54,7 +54,8 @@ def gpu_model(weights):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from ribodetector_b200.model import SeqModel
-    m = SeqModel(input_size=4, hidden_size=128, num_layers=1, num_classes=2, pack_seq=True)
+    m = SeqModel(input_size=4, hidden_size=128, num_layers=1, num_classes=2, pack_seq=True,
+                 precision="tc_exact")      # tests that exercise the other precisions name them
     m.load_state_dict(weights)
     m.to("cuda:0").eval()
     yield m

@@ -294,3 +294,34 @@ def test_gz_stream_reader_matches_gzip_module(tmp_path):
     (tmp_path / "bad.fq.gz").write_bytes(bytes(bad))
     with pytest.raises(ValueError):
         read_all(tmp_path / "bad.fq.gz", 1 << 20)
+
+
+def test_fastx_reader_memory_stays_bounded_for_small_chunks(tmp_path):
+    """with max_records x record_bytes far below the block size the reader used to carry (and double) an
+    ever larger tail.  Buffers must stay within block_bytes, every chunk but the last must hold exactly max_records
+    records, and the records must come out unchanged — FASTA and FASTQ."""
+    rng = np.random.default_rng(5)
+    n = 60000
+    seqs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(l))) for l in rng.integers(40, 90, size=n)]
+    fa = tmp_path / "small.fa"
+    fa.write_text("".join(">r%d\n%s\n" % (i, s) for i, s in enumerate(seqs)))
+    fq = tmp_path / "small.fq"
+    fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)) for i, s in enumerate(seqs)))
+    for path, width in ((fa, 2), (fq, 4)):
+        block = 1 << 20
+        with FastxReader(str(path), max_records=4096, block_bytes=block, threads=2) as rd:
+            got, sizes = [], []
+            for chunk in rd:
+                sizes.append(chunk.n)
+                got.extend(r[1] for r in chunk.records())
+                assert len(chunk.records()[0]) == width
+                chunk.release()
+            assert rd.peak_buffer_bytes <= block, rd.peak_buffer_bytes
+        assert got == seqs
+        assert all(s == 4096 for s in sizes[:-1]) and sum(sizes) == n
+    # a record larger than the block still grows the buffer instead of looping
+    big = tmp_path / "big.fa"
+    big.write_text(">x\n" + "ACGT" * 100000 + "\n>y\nAC\n")
+    with FastxReader(str(big), max_records=8, block_bytes=1 << 16) as rd:
+        recs = [r for c in rd for r in c.records()]
+    assert [len(r[1]) for r in recs] == [400000, 2]
