@@ -109,6 +109,7 @@ extern "C" int rd_create(int device,
     CK(cudaMalloc(&h->d_wout, sizeof(float) * 2 * 2 * RD_H));
     CK(cudaMalloc(&h->d_bout, sizeof(float) * 2));
     CK(cudaMalloc(&h->d_revlut, sizeof(float) * RD_MAX_LEN * 5 * 2));
+    CK(cudaMalloc(&h->d_lutstate, sizeof(double) * 2 * RD_H));
     CK(cudaMalloc(&h->d_hist, sizeof(int32_t) * (RD_MAX_LEN + 2)));
     CK(cudaMalloc(&h->d_cursor, sizeof(int32_t) * (RD_MAX_LEN + 2)));
     CK(cudaMalloc(&h->d_ctrl, sizeof(int32_t) * 8));
@@ -127,7 +128,7 @@ extern "C" int rd_create(int device,
         CK(cudaEventCreateWithFlags(&h->ev_out[s], cudaEventDisableTiming));
     }
     CK(cudaMalloc(&h->d_stage_counts, sizeof(int64_t) * 4));
-    int rc = rd_build_reverse_lut(h, nullptr, 0);
+    int rc = rd_build_reverse_lut(h, 512, 0);
     if (rc != RD_OK) return bail(rc);
     rc = rd_tc_create(h, w_hh_f, w_ih_f, b_ih_f, b_hh_f);
     if (rc != RD_OK) return bail(rc);
@@ -145,7 +146,7 @@ extern "C" void rd_destroy(rd_handle* h) {
     rd_fq_destroy(h);
     free_scratch(h);
     cudaFree(h->d_tab_f); cudaFree(h->d_tab_r); cudaFree(h->d_whh_t); cudaFree(h->d_whh_r_t);
-    cudaFree(h->d_wout); cudaFree(h->d_bout); cudaFree(h->d_revlut);
+    cudaFree(h->d_wout); cudaFree(h->d_bout); cudaFree(h->d_revlut); cudaFree(h->d_lutstate);
     cudaFree(h->d_hist); cudaFree(h->d_cursor); cudaFree(h->d_ctrl); cudaFree(h->d_blocksum);
     for (int e = 0; e < 2; ++e)
         for (int s = 0; s < rd_handle::NSTAGE; ++s) {
@@ -169,6 +170,8 @@ extern "C" void rd_destroy(rd_handle* h) {
 extern "C" int rd_reverse_lut(rd_handle* h, int kmax, float* out) {
     if (!h || !out || kmax < 0 || kmax >= RD_MAX_LEN) return fail(h, RD_ERR_INVALID, "rd_reverse_lut: bad arguments");
     RD_CUDA(h, cudaSetDevice(h->device));
+    int rc = rd_build_reverse_lut(h, kmax + 1, 0);
+    if (rc) return rc;
     RD_CUDA(h, cudaMemcpy(out, h->d_revlut, sizeof(float) * (kmax + 1) * 10, cudaMemcpyDeviceToHost));
     return RD_OK;
 }
@@ -239,6 +242,10 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
     const bool need_codes = precision == RD_PREC_FP32;
     int rc = ensure_scratch(h, n, max_len, need_codes);
     if (rc) return rc;
+    if (semantics == RD_SEM_PADDED && max_len > h->lut_rows) {      // krev < max_len: extend the reverse-direction table
+        rc = rd_build_reverse_lut(h, max_len, st);
+        if (rc) return rc;
+    }
     int64_t tiles = 0;
     {
         StageTimer tm(h, 0, st);

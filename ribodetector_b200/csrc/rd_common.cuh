@@ -56,7 +56,9 @@ struct rd_handle {
     float* d_whh_r_t = nullptr;    // [128][512]
     float* d_wout = nullptr;       // [2][256]
     float* d_bout = nullptr;       // [2]
-    float* d_revlut = nullptr;     // [RD_MAX_LEN][5][2] reverse-half logit contributions
+    float* d_revlut = nullptr;     // [RD_MAX_LEN][5][2] reverse-half logit contributions; rows [0, lut_rows) are built
+    double* d_lutstate = nullptr;  // [2][128] fp64 (h, c) of the reverse chain after lut_rows zero steps
+    int lut_rows = 0;
     rd_tc_state* tc = nullptr;
     rd_fq_state* fq = nullptr;
     bool simt_attr_set = false;
@@ -129,7 +131,7 @@ int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_prob
                    int64_t* d_counts, cudaStream_t st);
 int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n, int mode,
                    int8_t* d_labels, int64_t* d_counts, cudaStream_t st);
-int rd_build_reverse_lut(rd_handle* h, const float* d_wout_full, cudaStream_t st);
+int rd_build_reverse_lut(rd_handle* h, int rows, cudaStream_t st);      // extends the table to `rows` rows if shorter
 int rd_tc_create(rd_handle* h, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh);
 void rd_tc_destroy(rd_handle* h);
 void rd_fq_destroy(rd_handle* h);

@@ -1,23 +1,27 @@
-// rd_lstm_tc.cu — K2 on the 5th-generation tensor cores (RD_PREC_TC_FAST / RD_PREC_TC_EXACT).
+// rd_lstm_tc.cu — K2 on the 5th-generation tensor cores (RD_PREC_TC_FAST / TC_EXACT / TC_MIXED_RAW).
 //
 // Replaces `self.rnn(x, None)` + `last_items` + `self.out` (model/model.py:33-36) for the forward
 // direction; the reverse direction enters through the logit LUT (rd_tail.cu).
 //
 // One persistent CTA per SM owns one tile of 128 reads at a time (TMEM lane = read).  Per step t
 //     Z[128, 512] = [h_{t-1} | onehot(x_t), 1] . [W_hh ; W_ih ; b]^T          (tcgen05.mma, kind::f16)
-// with  A = h_{t-1} (+ the 16-wide one-hot/bias chunk) resident in TENSOR MEMORY, written there by the
-//           activation warps with tcgen05.st (fp16; EXACT: fp16 hi + fp16 lo residual),
+// with  A = h_{t-1} resident in TENSOR MEMORY, written there by the activation warps with tcgen05.st (fp16;
+//           EXACT: fp16 hi + fp16 lo residual; MIXED: fp16 hi + e5m2 hi + e5m2 lo residual), plus the 16-wide
+//           one-hot/bias chunk in shared memory,
 //       B = the recurrent weights, staged ONCE per CTA into shared memory by the TMA bulk-copy
 //           engine (cp.async.bulk) in the K-major SWIZZLE_NONE canonical layout,
-//       D = fp32 accumulators in tensor memory, produced in 4 column chunks of 128 (= 32 hidden
-//           units x 4 gates, gate-interleaved so one tcgen05.ld.32x32b.x32 hands a thread i,f,g,o of
-//           8 units of its read) through a ring of 2 chunk buffers (N = 128 is the smallest N at which a
-//           tcgen05.mma costs its ~78-cycle floor, tools/tc_rate.cu).
-// Sixteen activation warps (4 TMEM lane quarters x 4 unit-group lanes) drain the chunks: sigmoid/tanh,
-// cell update in fp32 registers, h_t back into the other A buffer; each reads its read's next base
-// straight from the caller's sequence bytes.  One elected lane of a warp-uniform warp issues the MMAs.  The recurrence is pipelined as a wavefront: chunk 0 of step t+1 accumulates K-chunk kc as
-// soon as the activation warps have published the 16 hidden units of K-chunk kc of step t
-// (h_ready[kc]), so the tensor pipe trails the activation pipe by one chunk instead of one step.
+//       D = fp32 accumulators in tensor memory, produced in 4 column chunks of 128 (= 32 hidden units x 4 gates)
+//           through a ring of 2 chunk buffers (N = 128 is the smallest N at which a tcgen05.mma costs its ~70-cycle
+//           floor, tools/tc_rate.cu).  Columns are laid out so that one tcgen05.ld.32x32b.x16 hands a thread i,f,g,o
+//           of 4 hidden units of its read (a "half-chunk"; see col_to_row).
+// Sixteen activation warps (4 TMEM lane quarters x 4 unit groups) drain the chunks half-chunk by half-chunk in a
+// software pipeline — the tcgen05.ld of the next half-chunk is in flight while the cells of the current one run:
+// ex2/rcp (or tanh) on the XU pipe, cell update in fp32 registers, h_t back into the other A buffer; each thread reads
+// its read's next base straight from the caller's sequence bytes.  One elected lane of a warp-uniform warp issues the
+// MMAs.  The recurrence is pipelined as a wavefront: chunk 0 of step t+1 accumulates K-chunk kc as soon as the
+// activation warps have published the 16 hidden units of K-chunk kc of step t (h_ready[kc]; the publish of a
+// half-chunk is deferred behind the next one's cells so that tcgen05.wait::st never stalls), so the tensor pipe
+// trails the activation pipe by one half-chunk instead of one step.
 //
 // FAST  : cta_group::1, one fp16 pass (9 MMAs of 128x128x16 per chunk), tanh.approx activations.
 // EXACT : cta_group::2 — a CTA pair shares the weights (each SM holds half of the N columns of
@@ -27,9 +31,11 @@
 // MIXED : the EXACT structure with the two correction passes in kind::f8f6f4 (e5m2, K = 32 per MMA): the fp16 main
 //         pass W_hi.h_hi plus ONE 8-bit pass over K = 256, [W_lo8 | W_hi8] . [h_hi8 ; h_lo8], i.e. 17 MMAs per chunk
 //         instead of 25.  The corrections are ~2^-12 of the products, so 3 significant bits keep them to ~2^-15:
-//         |dlogit| <= 2e-3 at 100 bp (measured ~1e-3 worst case, tests/test_gpu_parity.py), |dp| <= 1e-3.
+//         |dlogit| <= 3e-3, |dprob| <= 1e-3 at 100 bp (1.7e-3 / 7.6e-4 measured over 2^20 reads).
 //         h is carried as h * 2^-6 (free: the scale rides in the cell's last FMA) and W_hh as W * 2^6, which
 //         puts h_hi (as the top byte of its fp16), the fp16 residuals and the weights in e5m2's normal range.
+//         (e4m3 would halve the error but needs a 2^15 scale between the passes — scale-input-d, verified in
+//         tools/tc_probe8.cu — which rules out issuing main products before the last correction: DESIGN.md.)
 // See DESIGN.md for the layout tables and the roofline arithmetic.
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -52,12 +58,8 @@ __device__ unsigned long long g_tc_prof[16];
 #ifndef RD_TC_DEFER_PUBLISH
 #define RD_TC_DEFER_PUBLISH 1
 #endif
-#ifndef RD_TC_G_FAST
-#define RD_TC_G_FAST 4
-#endif
-#ifndef RD_TC_G_EXACT
+#define RD_TC_G_FAST 4          // unit-group warps per TMEM lane quarter (the activation loop is written for 4)
 #define RD_TC_G_EXACT 4
-#endif
 
 namespace {
 
@@ -155,22 +157,6 @@ __device__ __forceinline__ void tc_wait_st_after(uint32_t dep) {
     asm volatile("tcgen05.wait::st.sync.aligned; // %0" ::"r"(dep) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c),
-                 "r"(d) : "memory");
-}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(

@@ -170,39 +170,44 @@ codes_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, i
 
 // ---------------------------------------------------------------------------------------------
 // one-hot materialisation (parity artefact of the reference encoders)
-// Each thread writes 4 consecutive one-hot rows (64 B; 2 KB contiguous per warp) with streaming stores:
-// the output is written once and never re-read by this library.  One integer division per 4 rows.
+// A write-only stream of 16 B per base.  Every store instruction of a warp covers 32 CONSECUTIVE rows (512 contiguous
+// bytes = 4 full 128-B lines); a thread owns rows lane, lane + 32, ... of its warp's 256-row span, so 8 independent
+// streaming stores are in flight per thread.  One integer division per thread; the other rows follow by stepping.
+constexpr int OH_ROWS = 8;          // rows per thread
+__device__ __forceinline__ float4 onehot_row(uint32_t c) {
+    return make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f, c == 3u ? 1.f : 0.f);
+}
+
 __global__ void __launch_bounds__(256)
 onehot_padded_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int64_t n,
                      int L, float4* __restrict__ out) {
     const int64_t total = n * (int64_t)L;
-    const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (e0 >= total) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t r = warp * (32 * OH_ROWS) + lane;
+    if (r >= total) return;
     int64_t i;
     int t;
     if (total < ((int64_t)1 << 32)) {
-        const uint32_t q = (uint32_t)e0 / (uint32_t)L;
-        i = q; t = (int)((uint32_t)e0 - q * (uint32_t)L);
+        const uint32_t q = (uint32_t)r / (uint32_t)L;
+        i = q; t = (int)((uint32_t)r - q * (uint32_t)L);
     } else {
-        i = e0 / L; t = (int)(e0 - i * L);
+        i = r / L; t = (int)(r - i * L);
     }
     int64_t b = off[i];
     int64_t len = off[i + 1] - b;
-    float4 v[4];
-    int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (e0 + k < total) {
-            while (t >= L) { t -= L; ++i; b = off[i]; len = off[i + 1] - b; }
-            uint32_t c = 4u;
-            if ((int64_t)t < len) c = base_code(seq[b + t]);
-            v[k] = make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f, c == 3u ? 1.f : 0.f);
-            ++t; ++cnt;
+    for (int k = 0; k < OH_ROWS; ++k) {
+        if (r < total) {
+            if (t >= L) {
+                do { t -= L; ++i; } while (t >= L);
+                b = off[i]; len = off[i + 1] - b;
+            }
+            const uint32_t c = (int64_t)t < len ? base_code(seq[b + t]) : 4u;
+            __stcs(out + r, onehot_row(c));
         }
+        r += 32; t += 32;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (k < cnt) __stcs(out + e0 + k, v[k]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -266,22 +271,29 @@ rowoff_kernel(const int64_t* __restrict__ off, int64_t n, int L, const int64_t* 
     if (i == n - 1) row_off[n] = excl + v;
 }
 
+constexpr int OH_GROUP = 8;         // reads per warp in the ragged writer
 __global__ void __launch_bounds__(256)
 onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                      const int64_t* __restrict__ row_off, int64_t n, int L,
                      float4* __restrict__ out) {
-    // one warp per read, lanes stride over its bases: coalesced byte loads, 512-B stores
-    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (w >= n) return;
-    int64_t b = off[w];
-    int64_t len = off[w + 1] - b;
-    int m = (int)(len < L ? len : L);
-    int64_t ro = row_off[w];
-    for (int t = lane; t < m; t += 32) {
-        uint32_t c = base_code(seq[b + t]);
-        __stcs(out + ro + t, make_float4(c == 0u ? 1.f : 0.f, c == 1u ? 1.f : 0.f, c == 2u ? 1.f : 0.f,
-                                         c == 3u ? 1.f : 0.f));
+    // One warp per OH_GROUP consecutive reads: their rows are one contiguous range of the output, which the warp writes
+    // 32 consecutive rows (512 B) per store instruction whatever the read lengths (a warp per read left the last store
+    // of every 100-bp read with 4 of 32 lanes).  The group's row and byte offsets live in lanes 0..OH_GROUP and are
+    // handed around with shuffles.
+    const int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * OH_GROUP;
+    const int lane = threadIdx.x & 31;
+    if (w0 >= n) return;
+    const int g = (int)(n - w0 < OH_GROUP ? n - w0 : OH_GROUP);
+    const int64_t my_ro = row_off[w0 + (lane < g ? lane : g)];          // lanes >= g hold the group's end
+    const int64_t my_b = off[w0 + (lane < g ? lane : g)];
+    const int64_t begin = __shfl_sync(0xffffffffu, my_ro, 0), end = __shfl_sync(0xffffffffu, my_ro, g);
+    for (int64_t r0 = begin; r0 < end; r0 += 32) {
+        const int64_t r = r0 + lane;
+        int j = 0;
+#pragma unroll
+        for (int k = 1; k < OH_GROUP; ++k) j += (k < g && r >= __shfl_sync(0xffffffffu, my_ro, k)) ? 1 : 0;
+        const int64_t ro = __shfl_sync(0xffffffffu, my_ro, j), b = __shfl_sync(0xffffffffu, my_b, j);
+        if (r < end) __stcs(out + r, onehot_row(base_code(seq[b + (r - ro)])));
     }
 }
 
@@ -318,7 +330,7 @@ int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, i
     if (n == 0) return RD_OK;
     if (layout == RD_ONEHOT_PADDED) {
         int64_t total = n * (int64_t)L;
-        onehot_padded_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(
+        onehot_padded_kernel<<<(unsigned)((total + 256 * OH_ROWS - 1) / (256 * OH_ROWS)), 256, 0, st>>>(
             d_seq, d_off, n, L, reinterpret_cast<float4*>(d_out));
         h->launches += 1;
     } else {
@@ -338,7 +350,7 @@ int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, i
         rowlen_blocksum_kernel<<<(unsigned)nb, 256, 0, st>>>(d_off, n, L, h->d_blocksum);
         blocksum_scan_kernel<<<1, 1024, 0, st>>>(h->d_blocksum, nb);
         rowoff_kernel<<<(unsigned)nb, 256, 0, st>>>(d_off, n, L, h->d_blocksum, ro);
-        onehot_ragged_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(
+        onehot_ragged_kernel<<<(unsigned)(((n + OH_GROUP - 1) / OH_GROUP * 32 + 255) / 256), 256, 0, st>>>(
             d_seq, d_off, ro, n, L, reinterpret_cast<float4*>(d_out));
         h->launches += 4;
         if (tmp) {

@@ -68,14 +68,15 @@ __global__ void __launch_bounds__(RD_G4, 1)
 reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [128][512]
                    const float* __restrict__ tab_r,    // [5][512]
                    const float* __restrict__ wout,     // [2][256]
-                   int kmax_plus1, float* __restrict__ lut) {
+                   int k0, int k1, double* __restrict__ state,   // rows [k0, k1); state = (h, c) after k0 zero steps
+                   float* __restrict__ lut) {
     __shared__ double h[RD_H], c[RD_H];
     __shared__ double z[5][RD_G4];
     __shared__ double hrev[5][RD_H];
     const int j = threadIdx.x;                       // gate row
-    if (j < RD_H) { h[j] = 0.0; c[j] = 0.0; }
+    if (j < RD_H) { h[j] = k0 ? state[j] : 0.0; c[j] = k0 ? state[RD_H + j] : 0.0; }
     __syncthreads();
-    for (int k = 0; k < kmax_plus1; ++k) {
+    for (int k = k0; k < k1; ++k) {
         double dot = 0.0;
         for (int m = 0; m < RD_H; ++m) dot += (double)whh_r_t[m * RD_G4 + j] * h[m];
 #pragma unroll
@@ -105,6 +106,7 @@ reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [128][512]
         if (j < RD_H) { h[j] = h_next; c[j] = c_next; }
         __syncthreads();
     }
+    if (j < RD_H) { state[j] = h[j]; state[RD_H + j] = c[j]; }       // the chain resumes here when the table is extended
 }
 
 // ---- TC_AUTO: order-preserving compaction of the slots whose fast-pass margin is inside the band -------------
@@ -209,9 +211,15 @@ int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n
     return RD_OK;
 }
 
-int rd_build_reverse_lut(rd_handle* h, const float* /*unused*/, cudaStream_t st) {
-    reverse_lut_kernel<<<1, RD_G4, 0, st>>>(h->d_whh_r_t, h->d_tab_r, h->d_wout, RD_MAX_LEN, h->d_revlut);
+// The table is a serial chain of fp64 LSTM steps on one CTA (8.5 us per row): rd_create builds the rows every packed call
+// (row 0) and every padded call up to -l 512 needs; a padded call with a longer -l extends it from the saved state.
+int rd_build_reverse_lut(rd_handle* h, int rows, cudaStream_t st) {
+    if (rows > RD_MAX_LEN) rows = RD_MAX_LEN;
+    if (rows <= h->lut_rows) return RD_OK;
+    reverse_lut_kernel<<<1, RD_G4, 0, st>>>(h->d_whh_r_t, h->d_tab_r, h->d_wout, h->lut_rows, rows, h->d_lutstate, h->d_revlut);
     h->launches += 1;
+    h->lut_rows = rows;
     RD_CUDA(h, cudaGetLastError());
+    RD_CUDA(h, cudaStreamSynchronize(st));      // rare (first use of a longer -l): later calls may come on other streams
     return RD_OK;
 }
