@@ -406,7 +406,9 @@ def run_strong(R):
         r = model.classify_pairs_host(ts[0][0], off, ts[1][0], off, L, mode="rrna", out=out) if m else None
         torch.cuda.synchronize(R.dev)
         ms = (time.perf_counter() - t0) * 1e3
+        my_ms = ms
         (ms,) = R.max_over_ranks(ms)
+        (min_ms,) = [-v for v in R.max_over_ranks(-my_ms)]
         counts = (r["counts"] if r is not None else torch.zeros(3, dtype=torch.int64)).to(R.dev)
         shard.allreduce_counts(counts)                                  # NCCL: int64[3]
         gathered = shard.gather_labels(out["labels"].to(R.dev), P) if world > 1 else out["labels"]
@@ -431,6 +433,11 @@ def run_strong(R):
                 unpin(ts1)
                 res.update({"n1_reads_per_s_same_run": 2.0 * P / (ms1 / 1e3), "n1_ms": ms1,
                             "efficiency_vs_n1": ms1 / (world * ms),
+                            "rank_ms_min_max": [min_ms, ms], "overhead_ms_vs_n1_over_N": ms - ms1 / world,
+                            "limiter": "fixed cost per rd_classify_pairs_host call (first 2^18-read chunk's H2D and the last chunk's "
+                                       "D2H are not hidden behind kernels, pipeline fill/drain, last tiles of a shard partly "
+                                       "filled): it does not shrink with the shard.  Host feed is far from a limit: %.1f GB/s of "
+                                       "H2D over all ranks" % (P * (2 * L + 16) / (ms / 1e3) / 1e9),
                             "labels_equal_n1_bit_for_bit": bool(torch.equal(gathered.cpu(), out1["labels"])),
                             "counts_equal_n1": bool(r1["counts"].tolist() == counts.cpu().tolist())})
             else:

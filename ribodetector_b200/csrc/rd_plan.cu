@@ -271,29 +271,44 @@ rowoff_kernel(const int64_t* __restrict__ off, int64_t n, int L, const int64_t* 
     if (i == n - 1) row_off[n] = excl + v;
 }
 
-constexpr int OH_GROUP = 8;         // reads per warp in the ragged writer
 __global__ void __launch_bounds__(256)
 onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                      const int64_t* __restrict__ row_off, int64_t n, int L,
                      float4* __restrict__ out) {
-    // One warp per OH_GROUP consecutive reads: their rows are one contiguous range of the output, which the warp writes
-    // 32 consecutive rows (512 B) per store instruction whatever the read lengths (a warp per read left the last store
-    // of every 100-bp read with 4 of 32 lanes).  The group's row and byte offsets live in lanes 0..OH_GROUP and are
-    // handed around with shuffles.
-    const int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * OH_GROUP;
+    // The output rows of all reads form one contiguous range [0, row_off[n]).  Like the padded writer, a warp owns a span
+    // of 256 consecutive rows and every store instruction covers 32 consecutive rows (512 B) whatever the read lengths
+    // (a warp per read left the last store of every 100-bp read with 4 of 32 lanes).  The read holding a span's first
+    // row is found by a warp-wide 32-ary search in row_off (5 rounds for 2^22 reads); lanes then step forward.
     const int lane = threadIdx.x & 31;
-    if (w0 >= n) return;
-    const int g = (int)(n - w0 < OH_GROUP ? n - w0 : OH_GROUP);
-    const int64_t my_ro = row_off[w0 + (lane < g ? lane : g)];          // lanes >= g hold the group's end
-    const int64_t my_b = off[w0 + (lane < g ? lane : g)];
-    const int64_t begin = __shfl_sync(0xffffffffu, my_ro, 0), end = __shfl_sync(0xffffffffu, my_ro, g);
-    for (int64_t r0 = begin; r0 < end; r0 += 32) {
-        const int64_t r = r0 + lane;
-        int j = 0;
+    const int64_t total = row_off[n];
+    const int64_t n_spans = (total + 32 * OH_ROWS - 1) / (32 * OH_ROWS);
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    (void)L;                                          // rows beyond max_len do not exist in row_off
+    for (int64_t span = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; span < n_spans; span += n_warps) {
+        const int64_t base = span * (32 * OH_ROWS);
+        int64_t lo = 0, hi = n;                       // row_off[lo] <= base < row_off[hi]
+        while (hi - lo > 1) {
+            const int64_t width = hi - lo;
+            const int64_t p = lo + (((int64_t)(lane + 1) * width) >> 5);
+            const unsigned m = __ballot_sync(0xffffffffu, row_off[p] <= base);
+            const int c = __popc(m);                  // the predicate is monotone in the probe index
+            const int64_t nlo = c ? lo + (((int64_t)c * width) >> 5) : lo;
+            const int64_t nhi = c < 32 ? lo + (((int64_t)(c + 1) * width) >> 5) : hi;
+            lo = nlo; hi = nhi;
+        }
+        int64_t i = lo, r = base + lane;
+        int64_t ro = row_off[i], ro_next = row_off[i + 1], b = off[i];
 #pragma unroll
-        for (int k = 1; k < OH_GROUP; ++k) j += (k < g && r >= __shfl_sync(0xffffffffu, my_ro, k)) ? 1 : 0;
-        const int64_t ro = __shfl_sync(0xffffffffu, my_ro, j), b = __shfl_sync(0xffffffffu, my_b, j);
-        if (r < end) __stcs(out + r, onehot_row(base_code(seq[b + (r - ro)])));
+        for (int k = 0; k < OH_ROWS; ++k) {
+            if (r < total) {
+                if (r >= ro_next) {
+                    do { ++i; ro_next = row_off[i + 1]; } while (r >= ro_next);
+                    ro = row_off[i]; b = off[i];
+                }
+                __stcs(out + r, onehot_row(base_code(seq[b + (r - ro)])));
+            }
+            r += 32;
+        }
     }
 }
 
@@ -350,7 +365,7 @@ int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, i
         rowlen_blocksum_kernel<<<(unsigned)nb, 256, 0, st>>>(d_off, n, L, h->d_blocksum);
         blocksum_scan_kernel<<<1, 1024, 0, st>>>(h->d_blocksum, nb);
         rowoff_kernel<<<(unsigned)nb, 256, 0, st>>>(d_off, n, L, h->d_blocksum, ro);
-        onehot_ragged_kernel<<<(unsigned)(((n + OH_GROUP - 1) / OH_GROUP * 32 + 255) / 256), 256, 0, st>>>(
+        onehot_ragged_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, st>>>(
             d_seq, d_off, ro, n, L, reinterpret_cast<float4*>(d_out));
         h->launches += 4;
         if (tmp) {
