@@ -278,26 +278,31 @@ onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict_
     // The output rows of all reads form one contiguous range [0, row_off[n]).  Like the padded writer, a warp owns a span
     // of 256 consecutive rows and every store instruction covers 32 consecutive rows (512 B) whatever the read lengths
     // (a warp per read left the last store of every 100-bp read with 4 of 32 lanes).  The read holding a span's first
-    // row is found by a warp-wide 32-ary search in row_off (5 rounds for 2^22 reads); lanes then step forward.
+    // row is found by a warp-wide 32-ary search in row_off (5 rounds for 2^22 reads), once per warp: a warp walks a
+    // run of consecutive spans, its lanes stepping from read to read.
     const int lane = threadIdx.x & 31;
     const int64_t total = row_off[n];
     const int64_t n_spans = (total + 32 * OH_ROWS - 1) / (32 * OH_ROWS);
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t per_warp = (n_spans + n_warps - 1) / n_warps;          // a warp owns CONSECUTIVE spans: one search
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t span0 = warp * per_warp, span1 = span0 + per_warp < n_spans ? span0 + per_warp : n_spans;
     (void)L;                                          // rows beyond max_len do not exist in row_off
-    for (int64_t span = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; span < n_spans; span += n_warps) {
-        const int64_t base = span * (32 * OH_ROWS);
-        int64_t lo = 0, hi = n;                       // row_off[lo] <= base < row_off[hi]
-        while (hi - lo > 1) {
-            const int64_t width = hi - lo;
-            const int64_t p = lo + (((int64_t)(lane + 1) * width) >> 5);
-            const unsigned m = __ballot_sync(0xffffffffu, row_off[p] <= base);
-            const int c = __popc(m);                  // the predicate is monotone in the probe index
-            const int64_t nlo = c ? lo + (((int64_t)c * width) >> 5) : lo;
-            const int64_t nhi = c < 32 ? lo + (((int64_t)(c + 1) * width) >> 5) : hi;
-            lo = nlo; hi = nhi;
-        }
-        int64_t i = lo, r = base + lane;
-        int64_t ro = row_off[i], ro_next = row_off[i + 1], b = off[i];
+    if (span0 >= span1) return;
+    const int64_t base = span0 * (32 * OH_ROWS);
+    int64_t lo = 0, hi = n;                           // row_off[lo] <= base < row_off[hi]
+    while (hi - lo > 1) {
+        const int64_t width = hi - lo;
+        const int64_t p = lo + (((int64_t)(lane + 1) * width) >> 5);
+        const unsigned m = __ballot_sync(0xffffffffu, row_off[p] <= base);
+        const int c = __popc(m);                      // the predicate is monotone in the probe index
+        const int64_t nlo = c ? lo + (((int64_t)c * width) >> 5) : lo;
+        const int64_t nhi = c < 32 ? lo + (((int64_t)(c + 1) * width) >> 5) : hi;
+        lo = nlo; hi = nhi;
+    }
+    int64_t i = lo, r = base + lane;
+    int64_t ro = row_off[i], ro_next = row_off[i + 1], b = off[i];
+    for (int64_t span = span0; span < span1; ++span) {
 #pragma unroll
         for (int k = 0; k < OH_ROWS; ++k) {
             if (r < total) {
