@@ -180,21 +180,25 @@ record_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, int
 // ---- K4: label-partitioned record text ------------------------------------------------------------------
 __device__ __forceinline__ int label_class(int8_t l) { return l == 0 ? 0 : (l == 1 ? 1 : 2); }
 
-__device__ __forceinline__ int rec_text_len(const int64_t* __restrict__ rec, int64_t r) {
+// (nlines = 4: FASTQ "hdr\nseq\nplus\nqual\n"; nlines = 2: FASTA "hdr\nseq\n", the last two index slots hold other data)
+__device__ __forceinline__ int rec_text_len(const int64_t* __restrict__ rec, int64_t r, int nlines) {
     const longlong2* p = reinterpret_cast<const longlong2*>(rec + 8 * r);
-    const longlong2 a = p[0], b = p[1], c = p[2], d = p[3];
+    const longlong2 a = p[0], b = p[1];
+    if (nlines == 2) return (int)((a.y - a.x) + (b.y - b.x)) + 2;
+    const longlong2 c = p[2], d = p[3];
     return (int)((a.y - a.x) + (b.y - b.x) + (c.y - c.x) + (d.y - d.x)) + 4;
 }
 
 // per 256-record block: text bytes of each class
 __global__ void __launch_bounds__(256)
-part_sum_kernel(const int64_t* __restrict__ rec, const int8_t* __restrict__ labels, int64_t n, int64_t* __restrict__ blocksum) {
+part_sum_kernel(const int64_t* __restrict__ rec, const int8_t* __restrict__ labels, int64_t n, int64_t* __restrict__ blocksum,
+                int nlines) {
     __shared__ int64_t s[3][8];
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     int64_t v[3] = {0, 0, 0};
     if (r < n) {
         const int c = label_class(labels[r]);
-        const int l = rec_text_len(rec, r);
+        const int l = rec_text_len(rec, r, nlines);
         v[0] = c == 0 ? l : 0; v[1] = c == 1 ? l : 0; v[2] = c == 2 ? l : 0;
     }
 #pragma unroll
@@ -248,7 +252,7 @@ part_scan_kernel(int64_t* __restrict__ blocksum, int64_t nblk, int64_t* __restri
 // 256 records per CTA: in-block exclusive offsets per class, then half a warp per record writes its text
 __global__ void __launch_bounds__(256)
 part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ rec, const int8_t* __restrict__ labels,
-                 int64_t n, const int64_t* __restrict__ blockbase, uint8_t* __restrict__ out) {
+                 int64_t n, const int64_t* __restrict__ blockbase, uint8_t* __restrict__ out, int nlines) {
     __shared__ longlong2 s_rec[256][4];          // the block's slice of the record index: read from HBM once, coalesced
     __shared__ int64_t s_dst[256];
     __shared__ int s_wsum[3][8];
@@ -270,7 +274,8 @@ part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ re
     if (r < n) {
         cls = label_class(labels[r]);
         const longlong2 a = s_rec[tid][0], b = s_rec[tid][1], c = s_rec[tid][2], d = s_rec[tid][3];
-        len = (int)((a.y - a.x) + (b.y - b.x) + (c.y - c.x) + (d.y - d.x)) + 4;
+        len = nlines == 2 ? (int)((a.y - a.x) + (b.y - b.x)) + 2
+                          : (int)((a.y - a.x) + (b.y - b.x) + (c.y - c.x) + (d.y - d.x)) + 4;
     }
     int incl[3], mine[3];
 #pragma unroll
@@ -297,11 +302,13 @@ part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ re
         if (r0 + warp * 32 + 2 * i >= n) break;
         const int slot = warp * 32 + 2 * i + sub;
         if (r0 + slot >= n) continue;
-        const longlong2 a = s_rec[slot][0], b = s_rec[slot][1], c = s_rec[slot][2], d = s_rec[slot][3];
-        const int t0 = (int)(a.y - a.x) + 1, t1 = t0 + (int)(b.y - b.x) + 1, t2 = t1 + (int)(c.y - c.x) + 1,
-                  t3 = t2 + (int)(d.y - d.x) + 1;
+        const longlong2 a = s_rec[slot][0], b = s_rec[slot][1];
+        longlong2 c = s_rec[slot][2], d = s_rec[slot][3];
+        if (nlines == 2) { c = make_longlong2(0, 0); d = c; }
+        const int t0 = (int)(a.y - a.x) + 1, t1 = t0 + (int)(b.y - b.x) + 1;
+        const int t2 = nlines == 2 ? t1 : t1 + (int)(c.y - c.x) + 1, t3 = nlines == 2 ? t1 : t2 + (int)(d.y - d.x) + 1;
         uint8_t* o = out + s_dst[slot];
-        if (a.y + 1 == b.x && b.y + 1 == c.x && c.y + 1 == d.x) {
+        if (nlines == 4 && a.y + 1 == b.x && b.y + 1 == c.x && c.y + 1 == d.x) {
             // nothing was stripped: the record text is one contiguous range of the input plus the closing '\n'.
             // Copy it as 4-byte words aligned on the OUTPUT; the input words are realigned with a funnel shift.
             const uint8_t* src = buf + a.x;
@@ -431,7 +438,7 @@ static int launch_scan(rd_handle* h, rd_fq_state* s, int e, const uint8_t* d_buf
 }
 
 static int launch_partition(rd_handle* h, rd_fq_state* s, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
-                            const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, cudaStream_t st) {
+                            const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, cudaStream_t st, int nlines = 4) {
     if (n == 0) {
         RD_CUDA(h, cudaMemsetAsync(d_sizes3, 0, sizeof(int64_t) * 3, st));
         return RD_OK;
@@ -439,9 +446,9 @@ static int launch_partition(rd_handle* h, rd_fq_state* s, const uint8_t* d_buf, 
     const int64_t nblk = (n + 255) / 256;
     int rc = grow(h, &s->d_blocksum, &s->cap_blk, nblk * 3);
     if (rc) return rc;
-    part_sum_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_rec, d_labels, n, s->d_blocksum);
+    part_sum_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_rec, d_labels, n, s->d_blocksum, nlines);
     part_scan_kernel<<<1, 1024, 0, st>>>(s->d_blocksum, nblk, d_sizes3);
-    part_copy_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, d_rec, d_labels, n, s->d_blocksum, d_out);
+    part_copy_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, d_rec, d_labels, n, s->d_blocksum, d_out, nlines);
     h->launches += 3;
     RD_CUDA(h, cudaGetLastError());
     return RD_OK;
