@@ -250,6 +250,31 @@ int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64
                     int64_t* out_bytes2);
 int rd_fastq_collect(rd_handle* h, int slot, int64_t* sizes6, int64_t* counts3);
 
+/* ---- the same for FASTA text -----------------------------------------------------------------------------
+ * K0 for seq_parser's FASTA branch (fastx_parser.py:39-55) with rd_scan_fastx's semantics: lines strip()ped, blank
+ * ones skipped, a line starting with '>' opens a record, the other lines of a record are joined and UPPER-CASED; a
+ * record is complete when the next header (or, final_chunk != 0, the end of the text) is seen; at the end of the file a
+ * last header without sequence is dropped; sequence lines before the very first header stay attached to it.
+ * The joined sequences are written to d_buf[seq_base ..) — seq_base >= len, 16-byte aligned, d_buf holding at least
+ * seq_base + len bytes — so that a FASTA record looks like a FASTQ one to rd_classify_records:
+ *   d_rec int64[8] per record = [begin, end) of the header line (after strip) in d_buf, [begin, end) of the joined
+ *   sequence in d_buf (inside the region at seq_base), the offset of the record's first line, three unused slots.
+ * d_info (device int64[8]): [0] newlines seen, [1] records n, [2] consumed = offset of the first line not consumed,
+ * [3] bytes in the sequence region, [4] -1 or 4 * (line index) + 2 for a line of 4 MiB or more. */
+int rd_scan_fasta_device(rd_handle* h, uint8_t* d_buf, int64_t len, int64_t seq_base, int final_chunk,
+                         int64_t max_records, int64_t* d_rec, int64_t* d_info, void* stream);
+
+/* K4 for FASTA records: "header\nSEQUENCE\n" of every record, grouped [non-rRNA | rRNA | unclassified], input order
+ * inside a group (detect.py:680,601-663 with the 2-tuple records of fastx_parser.py:53-55). */
+int rd_partition_fasta_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
+                              const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, void* stream);
+
+/* rd_fastq_submit for blocks of FASTA text (same slots, collected with rd_fastq_collect; out_e needs len_e + 2). */
+int rd_fasta_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
+                    int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
+                    int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records, int64_t* consumed2,
+                    int64_t* out_bytes2);
+
 #ifdef __cplusplus
 }
 #endif

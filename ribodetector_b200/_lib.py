@@ -48,6 +48,9 @@ SIGNATURES = {
     "rd_partition_records_device": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "rd_fastq_submit": (_i, [_vp, _i, _i, _vp, _i64, _vp, _i64, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rd_fastq_collect": (_i, [_vp, _i, _vp, _vp]),
+    "rd_scan_fasta_device": (_i, [_vp, _vp, _i64, _i64, _i, _i64, _vp, _vp, _vp]),
+    "rd_partition_fasta_device": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "rd_fasta_submit": (_i, [_vp, _i, _i, _vp, _i64, _vp, _i64, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,5 +1,5 @@
-// rd_fastq_dev.cu — the edges of the path on the device: FASTQ text resident in HBM
-// → record index (K0), labels → label-partitioned record text (K4), and the host-buffer streaming form
+// rd_fastq_dev.cu — the edges of the path on the device: FASTQ (and FASTA) text resident in
+// HBM → record index (K0), labels → label-partitioned record text (K4), and the host-buffer streaming form
 // that chains  H2D → K0 → K1..K3 → K4 → D2H  over two slots.
 //
 // Replaces, for uncompressed FASTQ text,
@@ -177,6 +177,207 @@ record_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, int
     o[3] = make_longlong2(v[6], v[7]);
 }
 
+// ---- K0 for FASTA text ---------------------------------------------------------------------------------------
+// seq_parser's FASTA branch (fastx_parser.py:39-55): lines strip()ped, blank ones skipped, a line starting with '>' opens
+// a record, the other lines of a record are joined and upper-cased; a record is complete when the next header (or the
+// end of the file) is seen; at the end of the file a header without sequence is dropped; sequence lines before the very
+// first header stay attached to it.  On the device: newline index (nl_index_kernel, as for FASTQ) → one thread per line
+// (fa_line_kernel: strip, classify) → a two-component scan over the lines (headers so far = record id, sequence bytes so
+// far = where the line's bases go) → fa_emit_kernel writes the record index, fa_copy_kernel the joined upper-cased
+// sequences into the region BEHIND the text in the same buffer, so that a FASTA record looks like a FASTQ one to the
+// classify and partition kernels:  rec[r] = { hdr [b,e) , seq [b,e) (in the region at seq_base) , raw line begin, -, -, - }.
+constexpr unsigned long long FA_HDR = 1ull << 63, FA_SEQ = 1ull << 62;      // line descriptor: type | len << 40 | begin
+constexpr int FA_LEN_BITS = 22;                                             // a stripped line holds < 4 Mi bytes
+
+// lines the chunk is scanned over: every complete line that fits the line index, plus an unterminated last line at the
+// end of the file; *final_eff = the scanned lines really end the file (a chunk with more lines than the index holds is
+// handled like a chunk cut short: its remaining text comes round again)
+__device__ __forceinline__ int64_t fa_lines(const uint8_t* buf, int64_t len, int final_chunk, int64_t cap, const int64_t* info,
+                                            int64_t* n_nl_out, bool* final_eff) {
+    const bool all = info[0] <= cap;
+    const int64_t n_nl = all ? info[0] : cap;
+    *final_eff = final_chunk && all;
+    *n_nl_out = n_nl;
+    return n_nl + ((*final_eff && len > 0 && buf[len - 1] != '\n') ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256)
+fa_line_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, const unsigned long long* __restrict__ line_end,
+               unsigned long long* __restrict__ line_desc, int64_t cap, int64_t* __restrict__ info) {
+    int64_t n_nl; bool fin;
+    const int64_t n_lines = fa_lines(buf, len, final_chunk, cap, info, &n_nl, &fin);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    int64_t b = i == 0 ? 0 : (int64_t)(line_end[i - 1] & LE_POS) + 1;
+    int64_t x = i < n_nl ? (int64_t)(line_end[i] & LE_POS) : len;
+    while (x > b && py_space(buf[x - 1])) --x;                              // line.strip()
+    while (b < x && py_space(buf[b])) ++b;
+    unsigned long long d = (unsigned long long)b;
+    if (x > b) {
+        if (x - b >= ((int64_t)1 << FA_LEN_BITS)) atomicMin(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)(i * 4 + 2));
+        d |= (unsigned long long)(x - b) << 40;
+        d |= buf[b] == '>' ? FA_HDR : FA_SEQ;
+    }
+    line_desc[i] = d;
+}
+
+__device__ __forceinline__ int fa_len(unsigned long long d) { return (int)((d >> 40) & ((1u << FA_LEN_BITS) - 1)); }
+
+// per 256-line block: {headers, sequence bytes}
+__global__ void __launch_bounds__(256)
+fa_sum_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, int64_t cap, const int64_t* __restrict__ info,
+              const unsigned long long* __restrict__ line_desc, int64_t* __restrict__ blocksum) {
+    __shared__ int64_t s[2][8];
+    int64_t n_nl; bool fin;
+    const int64_t n_lines = fa_lines(buf, len, final_chunk, cap, info, &n_nl, &fin);
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const unsigned long long d = i < n_lines ? line_desc[i] : 0ull;
+    int64_t v[2] = {(d & FA_HDR) ? 1 : 0, (d & FA_SEQ) ? fa_len(d) : 0};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], k);
+        if ((threadIdx.x & 31) == 0) s[c][threadIdx.x >> 5] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int64_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s[threadIdx.x][w];
+        blocksum[(int64_t)blockIdx.x * 2 + threadIdx.x] = t;
+    }
+}
+
+// one CTA: exclusive scan of the block sums; then the chunk's record count and `consumed`
+//   info: [0] newlines (in), [1] records n, [2] consumed, [3] sequence bytes of the n records' region, [4] error,
+//         [5] headers in the chunk, [6] lines
+__global__ void __launch_bounds__(1024)
+fa_scan_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk_in, int64_t cap, int64_t* __restrict__ blocksum,
+               int64_t nblk, int64_t max_records, int64_t* __restrict__ info) {
+    __shared__ int64_t part[1024];
+    int64_t n_nl; bool fin;
+    const int64_t n_lines = fa_lines(buf, len, final_chunk_in, cap, info, &n_nl, &fin);
+    const int final_chunk = fin ? 1 : 0;
+    __shared__ int64_t total[2];
+    const int tid = threadIdx.x;
+    const int64_t per = (nblk + 1023) / 1024;
+    const int64_t lo = tid * per, hi = lo + per < nblk ? lo + per : nblk;
+    for (int c = 0; c < 2; ++c) {
+        int64_t sum = 0;
+        for (int64_t i = lo; i < hi; ++i) sum += blocksum[i * 2 + c];
+        part[tid] = sum;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            const int64_t o = tid >= d ? part[tid - d] : 0;
+            __syncthreads();
+            part[tid] += o;
+            __syncthreads();
+        }
+        int64_t run = part[tid] - sum;
+        if (tid == 1023) total[c] = part[1023];
+        __syncthreads();
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t v = blocksum[i * 2 + c];
+            blocksum[i * 2 + c] = run;
+            run += v;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int64_t headers = total[0];
+        // the record opened by the chunk's last header is complete only at the end of the file
+        int64_t n = final_chunk ? headers : (headers > 0 ? headers - 1 : 0);
+        if (final_chunk && headers == 0 && total[1] > 0) n = 1;            // header-less sequence: one record, '' header
+        if (n > max_records) n = max_records;
+        info[1] = n;                                                        // (fa_emit_kernel drops a trailing empty record)
+        info[3] = total[1];
+        info[5] = headers;
+        info[6] = n_lines;
+        // every header's record taken (only at the end of the file): all of the text is consumed; otherwise fa_emit_kernel
+        // stores the line start of header n, the first record left for the next chunk
+        info[2] = (n >= headers && (n > 0 || fin)) ? len : 0;
+        info[7] = n_nl;
+    }
+}
+
+// per line: record id and sequence offset from the scans; headers write the index, sequence lines are copied by
+// fa_copy_kernel.  seq_base = offset of the sequence region inside buf.
+__global__ void __launch_bounds__(256)
+fa_emit_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk_in, int64_t cap,
+               const unsigned long long* __restrict__ line_desc, const unsigned long long* __restrict__ line_end,
+               const int64_t* __restrict__ blocksum, int64_t seq_base, int64_t* __restrict__ rec, int64_t rec_cap,
+               int64_t* __restrict__ seq_at, int64_t* __restrict__ info) {
+    __shared__ int64_t s_w[2][8];
+    int64_t n_nl; bool fin;
+    const int64_t n_lines = fa_lines(buf, len, final_chunk_in, cap, info, &n_nl, &fin);
+    const int final_chunk = fin ? 1 : 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    const unsigned long long d = i < n_lines ? line_desc[i] : 0ull;
+    const int64_t mine[2] = {(d & FA_HDR) ? 1 : 0, (d & FA_SEQ) ? fa_len(d) : 0};
+    int64_t incl[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        int64_t v = mine[c];
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const int64_t o = __shfl_up_sync(0xffffffffu, v, k);
+            if (lane >= k) v += o;
+        }
+        incl[c] = v;
+        if (lane == 31) s_w[c][warp] = v;
+    }
+    __syncthreads();
+    int64_t ex[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        int64_t before = blocksum[(int64_t)blockIdx.x * 2 + c];
+        for (int w = 0; w < warp; ++w) before += s_w[c][w];
+        ex[c] = before + incl[c] - mine[c];                                 // headers / sequence bytes BEFORE this line
+    }
+    if (i >= n_lines) return;
+    const int64_t n = info[1], headers = info[5], total_seq = info[3];
+    if (i < n_lines) seq_at[i] = ex[1];                                     // where this line's bases go (fa_copy_kernel)
+    if (d & FA_HDR) {
+        const int64_t r = ex[0];                                            // this header opens record r
+        const int64_t b = (int64_t)(d & ((1ull << 40) - 1)), e = b + fa_len(d);
+        const int64_t raw = i == 0 ? 0 : (int64_t)(line_end[i - 1] & LE_POS) + 1;
+        if (r < rec_cap) {
+            rec[8 * r + 0] = b; rec[8 * r + 1] = e;
+            rec[8 * r + 2] = seq_base + (r == 0 ? 0 : ex[1]);              // lines before the first header stay with it
+            rec[8 * r + 4] = raw;
+            rec[8 * r + 5] = 0; rec[8 * r + 6] = 0; rec[8 * r + 7] = 0;
+            if (r == headers - 1) rec[8 * r + 3] = seq_base + total_seq;    // the chunk's last record ends with the region
+        }
+        if (r >= 1 && r - 1 < rec_cap) rec[8 * (r - 1) + 3] = seq_base + ex[1];
+        if (r == n) info[2] = raw;                                          // the first record not taken starts here
+        // at the end of the file a last record without sequence is dropped (fastx_parser.py:54)
+        if (final_chunk && r == headers - 1 && r == n - 1 && ex[1] == total_seq && !(r == 0 && total_seq > 0)) info[1] = n - 1;
+    }
+    if (headers == 0 && i == 0 && n == 1) {                                 // header-less sequence at the end of the file
+        rec[0] = 0; rec[1] = 0; rec[2] = seq_base; rec[3] = seq_base + total_seq; rec[4] = 0; rec[5] = rec[6] = rec[7] = 0;
+    }
+}
+
+// half a warp per sequence line: bases upper-cased into the sequence region
+__global__ void __launch_bounds__(256)
+fa_copy_kernel(uint8_t* __restrict__ buf, const unsigned long long* __restrict__ line_desc, const int64_t* __restrict__ seq_at,
+               const int64_t* __restrict__ info, int64_t seq_base, int64_t seq_limit) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int hl = threadIdx.x & 15;
+    if (i >= info[6]) return;
+    const unsigned long long d = line_desc[i];
+    if (!(d & FA_SEQ)) return;
+    const int64_t b = (int64_t)(d & ((1ull << 40) - 1));
+    const int l = fa_len(d);
+    const int64_t dst = seq_at[i];
+    if (dst + l > seq_limit) return;                                        // (cannot happen: the region is as large as the text)
+    uint8_t* o = buf + seq_base + dst;
+    for (int j = hl; j < l; j += 16) {
+        const uint8_t c = buf[b + j];
+        o[j] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c;              // .upper()
+    }
+}
+
 // ---- K4: label-partitioned record text ------------------------------------------------------------------
 __device__ __forceinline__ int label_class(int8_t l) { return l == 0 ? 0 : (l == 1 ? 1 : 2); }
 
@@ -351,6 +552,9 @@ struct rd_fq_state {
     unsigned long long* d_desc = nullptr; int64_t cap_desc = 0;
     int* d_ticket = nullptr;
     unsigned long long* d_line_end[2] = {nullptr, nullptr}; int64_t cap_lines[2] = {0, 0};
+    unsigned long long* d_line_desc[2] = {nullptr, nullptr}; int64_t cap_line_desc[2] = {0, 0};    // FASTA: per-line type/length/begin
+    int64_t* d_seq_at[2] = {nullptr, nullptr}; int64_t cap_seq_at[2] = {0, 0};                     // FASTA: per-line sequence offset
+    int64_t* d_fa_blocksum = nullptr; int64_t cap_fa_blk = 0;
     // partition scratch (s_cmp only)
     int64_t* d_blocksum = nullptr; int64_t cap_blk = 0;
     // streaming slots
@@ -391,7 +595,8 @@ void rd_fq_destroy(rd_handle* h) {
     if (!s) return;
     cudaFree(s->d_desc); cudaFree(s->d_ticket); cudaFree(s->d_blocksum); cudaFree(s->d_info);
     cudaFreeHost(s->h_info);
-    for (int e = 0; e < 2; ++e) { cudaFree(s->d_line_end[e]); cudaFree(s->d_logits[e]); }
+    for (int e = 0; e < 2; ++e) { cudaFree(s->d_line_end[e]); cudaFree(s->d_logits[e]); cudaFree(s->d_line_desc[e]); cudaFree(s->d_seq_at[e]); }
+    cudaFree(s->d_fa_blocksum);
     for (int i = 0; i < rd_fq_state::NSLOT; ++i) {
         for (int e = 0; e < 2; ++e) { cudaFree(s->d_buf[i][e]); cudaFree(s->d_out[i][e]); cudaFree(s->d_rec[i][e]); }
         cudaFree(s->d_labels[i]); cudaFree(s->d_res[i]); cudaFreeHost(s->h_res[i]);
@@ -454,7 +659,44 @@ static int launch_partition(rd_handle* h, rd_fq_state* s, const uint8_t* d_buf, 
     return RD_OK;
 }
 
+// FASTA: K0 over d_buf[0..len); the joined upper-cased sequences go to d_buf[seq_base ..) (seq_base >= len, capacity len)
+static int launch_scan_fasta(rd_handle* h, rd_fq_state* s, int e, uint8_t* d_buf, int64_t len, int64_t seq_base, int final_chunk,
+                             int64_t max_records, int64_t* d_rec, int64_t* d_info, cudaStream_t st) {
+    const int64_t ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    const int64_t cap = std::max<int64_t>(4, std::min<int64_t>(4 * max_records, len / 2 + 2));      // lines indexed
+    const int64_t nblk = (cap + 255) / 256;
+    int rc = grow(h, &s->d_desc, &s->cap_desc, ntiles);
+    if (!rc) rc = grow(h, &s->d_line_end[e], &s->cap_lines[e], cap);
+    if (!rc) rc = grow(h, &s->d_line_desc[e], &s->cap_line_desc[e], cap);
+    if (!rc) rc = grow(h, &s->d_seq_at[e], &s->cap_seq_at[e], cap);
+    if (!rc) rc = grow(h, &s->d_fa_blocksum, &s->cap_fa_blk, nblk * 2);
+    if (rc) return rc;
+    RD_CUDA(h, cudaMemsetAsync(d_info, 0, sizeof(int64_t) * 8, st));
+    RD_CUDA(h, cudaMemsetAsync(d_info + 4, 0xFF, sizeof(int64_t), st));            // "no bad line"
+    if (ntiles > 0) {
+        RD_CUDA(h, cudaMemsetAsync(s->d_desc, 0, sizeof(unsigned long long) * ntiles, st));
+        RD_CUDA(h, cudaMemsetAsync(s->d_ticket, 0, sizeof(int), st));
+        nl_index_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(d_buf, len, ntiles, s->d_desc, s->d_ticket,
+                                                                     s->d_line_end[e], cap, d_info);
+        h->launches += 1;
+    }
+    fa_line_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, len, final_chunk, s->d_line_end[e], s->d_line_desc[e], cap, d_info);
+    fa_sum_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, len, final_chunk, cap, d_info, s->d_line_desc[e], s->d_fa_blocksum);
+    fa_scan_kernel<<<1, 1024, 0, st>>>(d_buf, len, final_chunk, cap, s->d_fa_blocksum, nblk, max_records, d_info);
+    fa_emit_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, len, final_chunk, cap, s->d_line_desc[e], s->d_line_end[e],
+                                                   s->d_fa_blocksum, seq_base, d_rec, max_records, s->d_seq_at[e], d_info);
+    fa_copy_kernel<<<(unsigned)((cap * 16 + 255) / 256), 256, 0, st>>>(d_buf, s->d_line_desc[e], s->d_seq_at[e], d_info, seq_base, len);
+    h->launches += 5;
+    RD_CUDA(h, cudaGetLastError());
+    return RD_OK;
+}
+
 static int fq_fail(rd_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+static int parse_error_fasta(rd_handle* h, int64_t key) {
+    h->err = "FASTA: line " + std::to_string(key / 4 + 1) + " of the block holds 4 MiB or more (use --host_ingest)";
+    return RD_ERR_PARSE;
+}
 
 static int parse_error(rd_handle* h, int64_t key) {
     const int64_t r = key / 4;
@@ -477,6 +719,20 @@ extern "C" int rd_scan_fastq_device(rd_handle* h, const uint8_t* d_buf, int64_t 
     return launch_scan(h, s, 0, d_buf, len, final_chunk, max_records, d_rec, d_info, (cudaStream_t)stream);
 }
 
+extern "C" int rd_scan_fasta_device(rd_handle* h, uint8_t* d_buf, int64_t len, int64_t seq_base, int final_chunk,
+                                    int64_t max_records, int64_t* d_rec, int64_t* d_info, void* stream) {
+    if (!h) return RD_ERR_INVALID;
+    if (len < 0 || max_records < 0 || max_records > ((int64_t)1 << 30) || !d_info || (max_records && !d_rec) || (len && !d_buf) ||
+        seq_base < len)
+        return fq_fail(h, RD_ERR_INVALID, "rd_scan_fasta_device: bad arguments");
+    if (((uintptr_t)d_buf & 15) != 0) return fq_fail(h, RD_ERR_INVALID, "rd_scan_fasta_device: d_buf must be 16-byte aligned");
+    RD_CUDA(h, cudaSetDevice(h->device));
+    rd_fq_state* s = nullptr;
+    int rc = fq_state(h, &s);
+    if (rc) return rc;
+    return launch_scan_fasta(h, s, 0, d_buf, len, seq_base, final_chunk, max_records, d_rec, d_info, (cudaStream_t)stream);
+}
+
 extern "C" int rd_classify_records(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n, int max_len,
                                    int semantics, int precision, float* d_logits, float* d_probs, int8_t* d_labels,
                                    int64_t* d_counts, void* stream) {
@@ -491,8 +747,8 @@ extern "C" int rd_classify_records(rd_handle* h, const uint8_t* d_buf, const int
                               (cudaStream_t)stream, 8);
 }
 
-extern "C" int rd_partition_records_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
-                                           const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, void* stream) {
+static int partition_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n, const int8_t* d_labels,
+                            uint8_t* d_out, int64_t* d_sizes3, void* stream, int nlines) {
     if (!h) return RD_ERR_INVALID;
     if (n < 0 || !d_sizes3 || (n && (!d_buf || !d_rec || !d_labels || !d_out)))
         return fq_fail(h, RD_ERR_INVALID, "rd_partition_records_device: bad arguments");
@@ -500,13 +756,24 @@ extern "C" int rd_partition_records_device(rd_handle* h, const uint8_t* d_buf, c
     rd_fq_state* s = nullptr;
     int rc = fq_state(h, &s);
     if (rc) return rc;
-    return launch_partition(h, s, d_buf, d_rec, n, d_labels, d_out, d_sizes3, (cudaStream_t)stream);
+    return launch_partition(h, s, d_buf, d_rec, n, d_labels, d_out, d_sizes3, (cudaStream_t)stream, nlines);
 }
 
-extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
-                               int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
-                               int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records,
-                               int64_t* consumed2, int64_t* out_bytes2) {
+extern "C" int rd_partition_records_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
+                                           const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, void* stream) {
+    return partition_device(h, d_buf, d_rec, n, d_labels, d_out, d_sizes3, stream, 4);
+}
+
+extern "C" int rd_partition_fasta_device(rd_handle* h, const uint8_t* d_buf, const int64_t* d_rec, int64_t n,
+                                         const int8_t* d_labels, uint8_t* d_out, int64_t* d_sizes3, void* stream) {
+    return partition_device(h, d_buf, d_rec, n, d_labels, d_out, d_sizes3, stream, 2);
+}
+
+static int fastx_submit(rd_handle* h, int format, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
+                        int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
+                        int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records,
+                        int64_t* consumed2, int64_t* out_bytes2) {
+    const bool fasta = format == RD_FMT_FASTA;
     if (!h) return RD_ERR_INVALID;
     if (slot < 0 || slot >= rd_fq_state::NSLOT || (ends != 1 && ends != 2) || len1 < 0 || (ends == 2 && len2 < 0) ||
         max_records < 1 || max_records > ((int64_t)1 << 30) || max_len < 1 || max_len > RD_MAX_LEN || !n_records ||
@@ -525,8 +792,10 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
     *n_records = 0;
     consumed2[0] = consumed2[1] = 0;
     out_bytes2[0] = out_bytes2[1] = 0;
+    int64_t seq_base[2] = {0, 0};                     // FASTA: the joined sequences live behind the text, in the same buffer
     for (int e = 0; e < ends; ++e) {
-        rc = grow(h, &s->d_buf[slot][e], &s->cap_buf[slot][e], lens[e] + 16);
+        seq_base[e] = (lens[e] + 15) & ~(int64_t)15;
+        rc = grow(h, &s->d_buf[slot][e], &s->cap_buf[slot][e], fasta ? seq_base[e] + lens[e] + 16 : lens[e] + 16);
         if (!rc) rc = grow(h, &s->d_out[slot][e], &s->cap_out[slot][e], lens[e] + 16);
         if (!rc) rc = grow(h, &s->d_rec[slot][e], &s->cap_rec[slot][e], 8 * max_records);
         if (!rc) rc = grow(h, &s->d_logits[e], &s->cap_logits[e], 2 * max_records);
@@ -538,7 +807,9 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
     for (int e = 0; e < ends; ++e) {
         if (lens[e])
             RD_CUDA(h, cudaMemcpyAsync(s->d_buf[slot][e], bufs[e], (size_t)lens[e], cudaMemcpyHostToDevice, h->s_in));
-        rc = launch_scan(h, s, e, s->d_buf[slot][e], lens[e], final_chunk, max_records, s->d_rec[slot][e], s->d_info + 8 * e, h->s_in);
+        rc = fasta ? launch_scan_fasta(h, s, e, s->d_buf[slot][e], lens[e], seq_base[e], final_chunk, max_records,
+                                       s->d_rec[slot][e], s->d_info + 8 * e, h->s_in)
+                   : launch_scan(h, s, e, s->d_buf[slot][e], lens[e], final_chunk, max_records, s->d_rec[slot][e], s->d_info + 8 * e, h->s_in);
         if (rc) return rc;
     }
     RD_CUDA(h, cudaMemcpyAsync(s->h_info, s->d_info, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost, h->s_in));
@@ -547,6 +818,7 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
     if (ends == 2) n = std::min(n, s->h_info[8 + 1]);
     for (int e = 0; e < ends; ++e) {
         const int64_t bad = s->h_info[8 * e + 4];
+        if (bad >= 0 && fasta) return parse_error_fasta(h, bad);
         if (bad >= 0 && bad / 4 < n) return parse_error(h, bad);
         consumed2[e] = s->h_info[8 * e + 2];
     }
@@ -554,6 +826,12 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
         for (int e = 0; e < 2; ++e)
             if (s->h_info[8 * e + 1] > n) {           // this end holds more records than its mate: give the extra ones back
                 if (n == 0) { consumed2[e] = 0; continue; }
+                if (fasta) {                          // record n of this end starts at the raw line begin kept in its index entry
+                    RD_CUDA(h, cudaMemcpyAsync(s->h_info + 16, s->d_rec[slot][e] + (8 * n + 4), sizeof(int64_t), cudaMemcpyDeviceToHost, h->s_in));
+                    RD_CUDA(h, cudaStreamSynchronize(h->s_in));
+                    consumed2[e] = s->h_info[16];
+                    continue;
+                }
                 RD_CUDA(h, cudaMemcpyAsync(s->h_info + 16, s->d_line_end[e] + (4 * n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->s_in));
                 RD_CUDA(h, cudaStreamSynchronize(h->s_in));
                 consumed2[e] = (int64_t)((unsigned long long)s->h_info[16] & ((1ull << 62) - 1)) + 1;
@@ -579,14 +857,15 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
     }
     for (int e = 0; e < ends; ++e) {
         rc = launch_partition(h, s, s->d_buf[slot][e], s->d_rec[slot][e], n, s->d_labels[slot], s->d_out[slot][e],
-                              s->d_res[slot] + 3 * e, h->s_cmp);
+                              s->d_res[slot] + 3 * e, h->s_cmp, fasta ? 2 : 4);
         if (rc) return rc;
     }
     RD_CUDA(h, cudaEventRecord(s->ev_cmp[slot], h->s_cmp));
     RD_CUDA(h, cudaStreamWaitEvent(h->s_out, s->ev_cmp[slot], 0));
     for (int e = 0; e < ends; ++e) {
         // the text of n records is at most the bytes they took in the block (+1: an open last line gains its '\n')
-        out_bytes2[e] = std::min<int64_t>(consumed2[e] + 1, lens[e] + 1);
+        // (FASTA: "hdr\nSEQ\n" is never longer than the lines it came from, except for a header-less record: + 2)
+        out_bytes2[e] = std::min<int64_t>(consumed2[e] + (fasta ? 2 : 1), lens[e] + (fasta ? 2 : 1));
         RD_CUDA(h, cudaMemcpyAsync(outs[e], s->d_out[slot][e], (size_t)out_bytes2[e], cudaMemcpyDeviceToHost, h->s_out));
     }
     if (labels) RD_CUDA(h, cudaMemcpyAsync(labels, s->d_labels[slot], (size_t)n, cudaMemcpyDeviceToHost, h->s_out));
@@ -594,6 +873,22 @@ extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* 
     RD_CUDA(h, cudaEventRecord(s->ev_out[slot], h->s_out));
     s->pending[slot] = true;
     return RD_OK;
+}
+
+extern "C" int rd_fastq_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
+                               int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
+                               int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records,
+                               int64_t* consumed2, int64_t* out_bytes2) {
+    return fastx_submit(h, RD_FMT_FASTQ, slot, ends, buf1, len1, buf2, len2, final_chunk, max_records, max_len, semantics, precision,
+                        mode, out1, out2, labels, n_records, consumed2, out_bytes2);
+}
+
+extern "C" int rd_fasta_submit(rd_handle* h, int slot, int ends, const uint8_t* buf1, int64_t len1, const uint8_t* buf2,
+                               int64_t len2, int final_chunk, int64_t max_records, int max_len, int semantics, int precision,
+                               int mode, uint8_t* out1, uint8_t* out2, int8_t* labels, int64_t* n_records,
+                               int64_t* consumed2, int64_t* out_bytes2) {
+    return fastx_submit(h, RD_FMT_FASTA, slot, ends, buf1, len1, buf2, len2, final_chunk, max_records, max_len, semantics, precision,
+                        mode, out1, out2, labels, n_records, consumed2, out_bytes2);
 }
 
 extern "C" int rd_fastq_collect(rd_handle* h, int slot, int64_t* sizes6, int64_t* counts3) {

@@ -1,4 +1,4 @@
-"""FASTQ file(s) → label-partitioned output files with the record scan and the partition ON THE DEVICE
+"""FASTQ or FASTA file(s) → label-partitioned output files with the record scan and the partition ON THE DEVICE
 (``rd_fastq_submit`` / ``rd_fastq_collect``, csrc/rd_fastq_dev.cu).
 
 The reference parses records one Python string at a time (``fastx_parser.py:15-47``), joins and routes
@@ -49,15 +49,16 @@ class FastqGpuStream:
         if self.ends not in (1, 2):
             raise ValueError("one or two input files")
         fmts = [get_seq_format(p) for p in self.inputs]
-        if any(not f.startswith("fq") for f in fmts):
-            raise ValueError("the device ingest path reads FASTQ only")
+        if len({f[:2] for f in fmts}) != 1:
+            raise ValueError("the input files must be all FASTQ or all FASTA")
+        self.fasta = fmts[0].startswith("fa")
         self.plain = [not f.endswith("gz") for f in fmts]
         self.max_len, self.mode, self.semantics, self.precision = int(max_len), mode, semantics, precision
         if block_bytes is None:                  # 256 MB blocks (~1.2 M 100-bp reads), less when the input is small
             est = max(os.path.getsize(p) * (1 if plain else 8) for p, plain in zip(self.inputs, self.plain))
             block_bytes = min(1 << 28, max(1 << 20, -(-(est + 4096) // (1 << 20)) * (1 << 20)))
         self.block_bytes = int(block_bytes)
-        self.max_records = max(1, self.block_bytes // 16)
+        self.max_records = max(1, self.block_bytes // (32 if self.fasta else 16))
         self.threads = max(1, min(int(threads), 16))
         self.num_seqs = 0
         self.counts = np.zeros(3, np.int64)
@@ -177,7 +178,7 @@ class FastqGpuStream:
                 busy["read"] += t1 - t0
                 n, consumed, _ = self.models[u.dev].fastq_submit(
                     u.slot, u.inp, fills, final, self.max_records, self.max_len, u.out, mode=self.mode,
-                    semantics=self.semantics, precision=self.precision)
+                    semantics=self.semantics, precision=self.precision, fasta=self.fasta)
                 busy["submit"] += time.perf_counter() - t1
                 tails = [u.inp[e][consumed[e]:fills[e]].copy() for e in range(ends)]
                 if n:
@@ -187,17 +188,21 @@ class FastqGpuStream:
                     if not final:             # every buffer is full or at end of file, and no record came out
                         if ends == 2 and any(self.eof):
                             raise RuntimeError("The two input files hold different numbers of reads.")
-                        raise RuntimeError("a FASTQ record does not fit the %d-byte block" % self.block_bytes)
+                        raise RuntimeError("a record does not fit the %d-byte block" % self.block_bytes)
                 if final and (n == 0 or not any(t.size for t in tails)):
                     # (a capped block leaves whole records behind: they go round again; a truncated last record is dropped)
                     # one end holding a further COMPLETE record (four lines; the last one may lack its newline) means the
                     # files differ in length, as the host path (_pair_chunks) reports
                     def lines(t):
                         return int((t == 10).sum()) + int(t.size > 0 and t[-1] != 10)
-                    if ends == 2 and any(lines(t) >= 4 for t in tails):
+
+                    def extra_record(t):              # FASTA: a header left over; FASTQ: four lines left over
+                        return bool((t == 62).any()) if self.fasta else lines(t) >= 4
+                    if ends == 2 and any(extra_record(t) for t in tails):
                         raise RuntimeError("The two input files hold different numbers of reads.")
-                    for t in tails:
-                        warn_if_truncated(t, int(self.counts.sum()))
+                    if not self.fasta:
+                        for t in tails:
+                            warn_if_truncated(t, int(self.counts.sum()))
                     break
         finally:
             inflight.put(None)

@@ -198,7 +198,7 @@ class Predictor:
                 colors.OKYELLOW, ", ".join(unc), colors.ENDC))
 
         if self._device_ingest():
-            # FASTQ text goes to the GPU as it is: record scan (K0) and label partition (K4) run there too
+            # the file text goes to the GPU as it is: record scan (K0) and label partition (K4) run there too
             from .data_loader.fastq_gpu import FastqGpuStream
             stream = FastqGpuStream(self.models, self.input, self.len, mode=self.args.ensure, semantics=self.semantics,
                                     precision=self.args.precision, threads=threads)
@@ -292,11 +292,13 @@ class Predictor:
         self._report(num_seqs, total, want_unc)
 
     def _device_ingest(self):
-        """FASTQ inputs (plain or gz) take the device ingest path unless --host_ingest asks for the host scanner."""
+        """FASTQ or FASTA inputs (plain or gz; all of one kind) take the device ingest path unless --host_ingest asks for
+        the host scanner."""
         from .data_loader import get_seq_format
         if getattr(self.args, "host_ingest", False) or self.chunk_size is not None:
             return False
-        return all(get_seq_format(f).startswith("fq") for f in self.input)
+        kinds = {get_seq_format(f)[:2] for f in self.input}
+        return len(kinds) == 1
 
     def _report(self, num_seqs, total, want_unc):
         self.num_seqs, self.num_nonrrna, self.num_rrna, self.num_unknown = num_seqs, int(total[0]), int(total[1]), int(total[2])

@@ -325,6 +325,48 @@ class SeqModel:
             raise ValueError("FASTQ: %s in record %d" % ("blank line" if info[4] % 4 == 1 else "header without '@'", info[4] // 4))
         return d_text, rec[:n], n, int(info[2])
 
+    def scan_fasta(self, text, final_chunk=True, max_records=None):
+        """FASTA text → (d_buf, rec int64[n, 8], n, consumed): like scan_fastq; d_buf is the text followed by the region
+        that holds the joined upper-cased sequences (rec[:, 2:4] index it).  fastx_parser.py:39-55."""
+        h = self._need()
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            text = torch.frombuffer(bytearray(text), dtype=torch.uint8) if len(text) else torch.empty(0, dtype=torch.uint8)
+        text = torch.as_tensor(text)
+        if text.dtype != torch.uint8:
+            raise ValueError("text must be uint8")
+        n_bytes = text.numel()
+        seq_base = (n_bytes + 15) & ~15
+        cap = int(max_records) if max_records is not None else n_bytes // 2 + 1
+        with torch.cuda.device(self._device):
+            d_buf = torch.empty(seq_base + n_bytes + 16, dtype=torch.uint8, device=self._device)
+            d_buf[:n_bytes] = text.to(self._device)
+            rec = torch.empty((max(cap, 1), 8), dtype=torch.int64, device=self._device)
+            info = torch.empty(8, dtype=torch.int64, device=self._device)
+            rc = self._lib.rd_scan_fasta_device(h, _ptr(d_buf), n_bytes, seq_base, int(bool(final_chunk)), cap,
+                                                _ptr(rec), _ptr(info), self._stream())
+        _lib.check(self._lib, h, rc, "rd_scan_fasta_device")
+        info = info.cpu().tolist()
+        if info[4] >= 0:
+            raise ValueError("FASTA: line %d holds 4 MiB or more" % (info[4] // 4 + 1))
+        n = int(info[1])
+        return d_buf, rec[:n], n, int(info[2])
+
+    def partition_fasta(self, d_buf, rec, labels):
+        """partition_records for FASTA records ("header\\nSEQUENCE\\n")."""
+        h = self._need()
+        n = rec.shape[0]
+        labels = torch.as_tensor(labels, dtype=torch.int8).to(self._device).contiguous()
+        if labels.numel() != n:
+            raise ValueError("labels/records mismatch")
+        with torch.cuda.device(self._device):
+            out = torch.empty(d_buf.numel() // 2 + 16, dtype=torch.uint8, device=self._device)
+            sizes = torch.zeros(3, dtype=torch.int64, device=self._device)
+            rc = self._lib.rd_partition_fasta_device(h, _ptr(d_buf) if n else None, _ptr(rec) if n else None, n,
+                                                     _ptr(labels) if n else None, _ptr(out), _ptr(sizes), self._stream())
+        _lib.check(self._lib, h, rc, "rd_partition_fasta_device")
+        sizes = sizes.cpu()
+        return out[:int(sizes.sum())], sizes
+
     def classify_records(self, d_text, rec, max_len, semantics=None, precision=None, counts=None):
         """rd_classify over the sequence lines of a record index → (logits[n,2], labels[n]) on the device."""
         h = self._need()
@@ -358,9 +400,10 @@ class SeqModel:
         return out[:int(sizes.sum())], sizes
 
     def fastq_submit(self, slot, bufs, lens, final_chunk, max_records, max_len, outs, labels=None, mode="none",
-                     semantics=None, precision=None):
-        """Streaming form: host FASTQ block(s) in (numpy uint8, one per end), host outs (numpy uint8, capacity
-        len + 1) filled by the time ``fastq_collect(slot)`` returns.  → (n_records, consumed[ends], out_bytes[ends])."""
+                     semantics=None, precision=None, fasta=False):
+        """Streaming form: host FASTQ (or, fasta=True, FASTA) block(s) in (numpy uint8, one per end), host outs (numpy
+        uint8, capacity len + 2) filled by the time ``fastq_collect(slot)`` returns.
+        → (n_records, consumed[ends], out_bytes[ends])."""
         h = self._need()
         ends = len(bufs)
         semantics = semantics or ("packed" if self.pack_seq else "padded")
@@ -369,7 +412,8 @@ class SeqModel:
         consumed = (ctypes.c_int64 * 2)()
         out_bytes = (ctypes.c_int64 * 2)()
         b2, l2, o2 = (_ptr(bufs[1]), int(lens[1]), _ptr(outs[1])) if ends == 2 else (None, 0, None)
-        rc = self._lib.rd_fastq_submit(h, int(slot), ends, _ptr(bufs[0]), int(lens[0]), b2, l2, int(bool(final_chunk)),
+        submit = self._lib.rd_fasta_submit if fasta else self._lib.rd_fastq_submit
+        rc = submit(h, int(slot), ends, _ptr(bufs[0]), int(lens[0]), b2, l2, int(bool(final_chunk)),
                                        int(max_records), int(max_len), _lib.SEM[semantics], _lib.PREC[precision],
                                        _lib.PAIR[mode], _ptr(outs[0]), o2, _ptr(labels), ctypes.byref(n),
                                        ctypes.cast(consumed, ctypes.c_void_p), ctypes.cast(out_bytes, ctypes.c_void_p))

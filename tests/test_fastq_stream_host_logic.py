@@ -37,7 +37,8 @@ class HostStandIn:
         return n, consumed.value, hdr, plus, qual, seq, off
 
     def fastq_submit(self, slot, bufs, lens, final_chunk, max_records, max_len, outs, labels=None, mode="none",
-                     semantics=None, precision=None):
+                     semantics=None, precision=None, fasta=False):
+        assert not fasta
         assert slot not in self.slots, "slot resubmitted before it was collected"
         self.submits += 1
         scans = [self._scan(b, int(l), final_chunk, max_records) for b, l in zip(bufs, lens)]
@@ -143,8 +144,8 @@ def test_error_paths(tmp_path):
     (tmp_path / "long.fq").write_bytes(b"@r\n" + b"A" * 5000 + b"\n+\n" + b"I" * 5000 + b"\n")
     with pytest.raises(RuntimeError, match="does not fit"):
         FastqGpuStream([HostStandIn()], [str(tmp_path / "long.fq")], 100, block_bytes=1024).run(sinks)
-    with pytest.raises(ValueError):
-        FastqGpuStream([HostStandIn()], [str(tmp_path / "x.fa")], 100)
+    with pytest.raises(ValueError):                       # one kind of input per run: FASTQ and FASTA do not mix
+        FastqGpuStream([HostStandIn()], [str(tmp_path / "r1.fq"), str(tmp_path / "x.fa")], 100)
     (tmp_path / "empty.fq").write_bytes(b"")
     st = FastqGpuStream([HostStandIn()], [str(tmp_path / "empty.fq")], 100)
     st.run(sinks)
