@@ -368,10 +368,13 @@ static int classify_host_impl(rd_handle* h, int ends,
     if (!labels) return fail(h, RD_ERR_INVALID, "rd_classify_host: labels is required");
     RD_CUDA(h, cudaSetDevice(h->device));
 
-    const int64_t chunk = std::min<int64_t>(CHUNK_READS, n);
+    // (a chunk is ~2 Mi READS whatever the number of ends: a pair chunk holds half as many units, so that a 2 Mi-pair
+    //  call is still cut into pieces whose copies hide behind the kernels of the piece before)
+    const int64_t chunk_cap = CHUNK_READS / ends;
+    const int64_t chunk = std::min<int64_t>(chunk_cap, n);
     std::vector<int64_t> cut;                                  // chunk c = reads [cut[c], cut[c+1])
     cut.push_back(0);
-    if (n > CHUNK_READS) cut.push_back(FIRST_CHUNK_READS);
+    if (n > chunk_cap) cut.push_back(FIRST_CHUNK_READS / ends);
     while (cut.back() < n) cut.push_back(std::min(n, cut.back() + chunk));
     int64_t max_bytes = 0;
     for (int e = 0; e < ends; ++e)
