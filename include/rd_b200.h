@@ -73,7 +73,10 @@ typedef struct rd_handle rd_handle;
  *   TC_MIXED : two passes like TC_AUTO — TC_MIXED_RAW over every read, then TC_EXACT over the reads whose margin is
  *              below RD_BAND_MIXED * s^2 (12x / 2.6x the largest margin error measured for the raw kernel at
  *              100 / 300 bp; 0.15 % / 1.5 % of random reads): LABELS equal TC_EXACT's, logits exact-grade inside the
- *              band and to the TC_MIXED_RAW tolerance outside it.  The default of the command line and of bench.py. */
+ *              band and to the TC_MIXED_RAW tolerance outside it.  The default of the command line and of bench.py.
+ *              (Pairs: the per-read guarantee carries over to the rrna / norrna / both rules, which combine per-end
+ *              LABELS; RD_PAIR_NONE takes the argmax of the SUM of the two ends' logits, detect.py:655-661, so its label
+ *              equals TC_EXACT's for every pair whose summed margin is outside twice the logit tolerance.) */
 #define RD_PREC_TC_MIXED 4
 #define RD_PREC_TC_MIXED_RAW 5
 #define RD_BAND_FAST  0.25f

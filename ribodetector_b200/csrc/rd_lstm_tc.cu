@@ -58,6 +58,14 @@ __device__ unsigned long long g_tc_prof[16];
 #ifndef RD_TC_DEFER_PUBLISH
 #define RD_TC_DEFER_PUBLISH 1
 #endif
+// measurement-only switches (tools/ab_bench.sh; results are garbage): run the kernel without its tensor-core work or
+// without its cell arithmetic, to see what each half costs in time, clock and power on its own
+#ifndef RD_TC_SKIP_MMA
+#define RD_TC_SKIP_MMA 0
+#endif
+#ifndef RD_TC_SKIP_CELLS
+#define RD_TC_SKIP_CELLS 0
+#endif
 #define RD_TC_G_FAST 4          // unit-group warps per TMEM lane quarter (the activation loop is written for 4)
 #define RD_TC_G_EXACT 4
 
@@ -445,7 +453,8 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
     if (warp == EPI_WARPS) {
         // ============ MMA issuer (leader CTA; warp-uniform control flow, one elected lane issues) ============
         if (rank == 0) {
-            const bool elected = elect_one();
+            const bool elected_lane = elect_one();
+            const bool elected = elected_lane && !RD_TC_SKIP_MMA;        // (RD_TC_SKIP_MMA: only the commits are issued)
             mbar_wait(bar_w, 0);
             // (the peer's half of the weights has landed before its activation warps first arrive on
             //  bar_tile: they wait on their own bar_w first)
@@ -549,7 +558,7 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
                                 }
                             }
                         }
-                        if (elected) mma_commit<CG>(bar_full + 8 * buf);
+                        if (elected_lane) mma_commit<CG>(bar_full + 8 * buf);
                         __syncwarp();
 #ifdef RD_TC_PROFILE
                         if (mc == 2 && t > 0) {      // time from the chunk's first issue to its completion (perturbs the pipeline)
@@ -626,8 +635,9 @@ lstm_tc_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off,
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float cn;
-                        lstm_cell<MODE>(__uint_as_float(v[u]), __uint_as_float(v[4 + u]), __uint_as_float(v[8 + u]),
-                                        __uint_as_float(v[12 + u]), c[mc][half][u], cn, hv[u]);
+                        if (RD_TC_SKIP_CELLS) { cn = c[mc][half][u]; hv[u] = __uint_as_float(v[u] ^ v[4 + u] ^ v[8 + u] ^ v[12 + u]) * 1e-30f; }
+                        else lstm_cell<MODE>(__uint_as_float(v[u]), __uint_as_float(v[4 + u]), __uint_as_float(v[8 + u]),
+                                             __uint_as_float(v[12 + u]), c[mc][half][u], cn, hv[u]);
                         c[mc][half][u] = cn;     // (a read that has finished keeps stepping on zero rows: nothing reads its state)
                     }
                     if (any_last && last) {        // fused FC: this thread's units of W_out[:, :H] . h_fwd   (model.py:36)

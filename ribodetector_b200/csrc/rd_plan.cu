@@ -302,13 +302,16 @@ onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict_
     }
     int64_t i = lo, r = base + lane;
     int64_t ro = row_off[i], ro_next = row_off[i + 1], b = off[i];
+    // the next read's offsets are loaded one read ahead, so stepping into it costs no dependent load
+    int64_t ro_next2 = row_off[i + 2 <= n ? i + 2 : n], b_next = off[i + 1 <= n ? i + 1 : n];
     for (int64_t span = span0; span < span1; ++span) {
 #pragma unroll
         for (int k = 0; k < OH_ROWS; ++k) {
             if (r < total) {
-                if (r >= ro_next) {
-                    do { ++i; ro_next = row_off[i + 1]; } while (r >= ro_next);
-                    ro = row_off[i]; b = off[i];
+                while (r >= ro_next) {
+                    ++i; ro = ro_next; ro_next = ro_next2; b = b_next;
+                    ro_next2 = row_off[i + 2 <= n ? i + 2 : n];
+                    b_next = off[i + 1 <= n ? i + 1 : n];
                 }
                 __stcs(out + r, onehot_row(base_code(seq[b + (r - ro)])));
             }

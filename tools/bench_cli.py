@@ -43,8 +43,20 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
     L = int(sys.argv[2]) if len(sys.argv) > 2 else 100
     d = tempfile.mkdtemp(prefix="rdcli_")
-    inp = os.path.join(d, "in.fq")
-    size = write_fastq(inp, n, L, synth.SEED_BASE + 7)
+    fasta = bool(os.environ.get("RD_CLI_FASTA", ""))       # FASTA input (">r%09d" / sequence, one line each) instead of FASTQ
+    inp = os.path.join(d, "in.fa" if fasta else "in.fq")
+    if fasta:
+        seq, _ = synth.synth_reads_fixed(n, L, synth.SEED_BASE + 7)
+        rec = np.empty((n, 11 + L + 1), np.uint8)
+        rec[:, 0], rec[:, 1] = ord(">"), ord("r")
+        idx = np.arange(n)
+        for k in range(9):
+            rec[:, 2 + 8 - k] = ord("0") + (idx // 10 ** k) % 10
+        rec = np.concatenate([rec[:, :11], np.full((n, 1), 10, np.uint8), seq.reshape(n, L), np.full((n, 1), 10, np.uint8)], axis=1)
+        rec.tofile(inp)
+        size = rec.size
+    else:
+        size = write_fastq(inp, n, L, synth.SEED_BASE + 7)
     gz = os.environ.get("RD_CLI_GZ", "")                  # "bgzf": BGZF-framed input, "gzip": one plain gzip member
     if gz:
         text = np.fromfile(inp, np.uint8)
@@ -82,7 +94,7 @@ def main():
         dt = time.perf_counter() - t0
         print("       load_model %.2f s, detect %.2f s" % (t_load, dt - t_load))
         k = 2 if paired else 1                            # a pair counts as 2 reads
-        print("run %d: %d %s, %.2f GB FASTQ in %.2f s = %.2f M reads/s (non-rRNA %d, rRNA %d)"
+        print("run %d: %d %s, %.2f GB of text in %.2f s = %.2f M reads/s (non-rRNA %d, rRNA %d)"
               % (rep, pred.num_seqs, "pairs" if paired else "reads", size / 1e9, dt, k * n / dt / 1e6, pred.num_nonrrna, pred.num_rrna), flush=True)
         print("       stage busy seconds:", {k: round(v, 3) for k, v in pred.stage_seconds.items()},
               "page-locking: %.2f s" % getattr(pred, "setup_seconds", 0.0), flush=True)
