@@ -236,6 +236,11 @@ extern "C" int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int res
     return RD_OK;
 }
 
+static float band_tau(int precision, int max_len) {
+    const float len_scale = max_len > 100 ? (float)max_len / 100.0f : 1.0f;
+    return precision == RD_PREC_TC_AUTO ? RD_BAND_FAST * len_scale : RD_BAND_MIXED * len_scale * len_scale;
+}
+
 int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                            int semantics, int precision, float* d_logits, float* d_probs,
                            int8_t* d_labels, int64_t* d_counts, cudaStream_t st, int ostride) {
@@ -262,8 +267,7 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
             const bool fast = precision == RD_PREC_TC_AUTO;
             // (the error of a recurrence grows with its length: linearly for the fast mode's bound, and the largest margin
             //  error of the mixed kernel over 2^20 reads per length grows like the square: profiles/r2_prec_err_big.txt)
-            const float len_scale = max_len > 100 ? (float)max_len / 100.0f : 1.0f;
-            const float tau = fast ? RD_BAND_FAST * len_scale : RD_BAND_MIXED * len_scale * len_scale;
+            const float tau = band_tau(precision, max_len);
             rc = ensure_band(h);
             if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, fast ? RD_PREC_TC_FAST : RD_PREC_TC_MIXED_RAW, d_logits, st,
                                             nullptr, nullptr, nullptr, ostride);
@@ -277,6 +281,22 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
     if (d_probs || d_labels || d_counts) {
         StageTimer tm(h, 2, st);
         rc = rd_launch_tail(h, d_logits, n, d_probs, d_labels, d_counts, st);
+    }
+    return rc;
+}
+
+int rd_pair_none_refine(rd_handle* h, const uint8_t* const d_seq[2], const int64_t* const d_off[2], int64_t n, int max_len,
+                        int semantics, int precision, float* const d_logits[2], cudaStream_t st, int ostride) {
+    if (n == 0 || (precision != RD_PREC_TC_AUTO && precision != RD_PREC_TC_MIXED)) return RD_OK;
+    const float tau = 2.0f * band_tau(precision, max_len);          // two first-pass margins add up
+    int rc = ensure_band(h);
+    for (int e = 0; e < 2 && !rc; ++e) {
+        int64_t tiles = 0;
+        rc = rd_launch_plan(h, d_seq[e], d_off[e], n, max_len, semantics, false, &tiles, st, ostride);   // (the ends share the scratch)
+        if (!rc) rc = rd_launch_band_select(h, d_logits[e], tiles, tau, st, d_logits[1 - e]);
+        const int64_t nb = (tiles * RD_TILE + 255) / 256;
+        if (!rc) rc = rd_launch_lstm_tc(h, d_seq[e], d_off[e], tiles, max_len, RD_PREC_TC_EXACT, d_logits[e], st, h->d_splan2,
+                                        h->d_perm2, h->d_band + nb, ostride);
     }
     return rc;
 }
@@ -428,6 +448,13 @@ static int classify_host_impl(rd_handle* h, int ends,
             for (int e = 0; e < 2; ++e) {
                 rc = rd_classify_device(h, h->d_stage_seq[e][st], h->d_stage_off[e][st], m, max_len, semantics,
                                      precision, h->d_stage_logits[e][st], nullptr, nullptr, nullptr, h->s_cmp);
+                if (rc) return rc;
+            }
+            if (mode == RD_PAIR_NONE) {
+                const uint8_t* sq[2] = {h->d_stage_seq[0][st], h->d_stage_seq[1][st]};
+                const int64_t* of[2] = {h->d_stage_off[0][st], h->d_stage_off[1][st]};
+                float* lg[2] = {h->d_stage_logits[0][st], h->d_stage_logits[1][st]};
+                rc = rd_pair_none_refine(h, sq, of, m, max_len, semantics, precision, lg, h->s_cmp);
                 if (rc) return rc;
             }
             rc = rd_launch_pair(h, h->d_stage_logits[0][st], h->d_stage_logits[1][st], m, mode,

@@ -126,7 +126,12 @@ int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, 
 int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len, int semantics,
                        int precision, float* d_logits, float* d_probs, int8_t* d_labels, int64_t* d_counts,
                        cudaStream_t st, int ostride = 1);      // K1 -> K2 -> K3 on `st`, scratch grown on demand
-int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st);
+int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st,
+                          const float* d_mate_logits = nullptr);      // mate != NULL: band on the pair's summed margin
+// RD_PAIR_NONE under a two-pass precision: re-run in TC_EXACT both ends of the pairs whose SUMMED first-pass margin is
+// inside the band (detect.py:655-661 decides on the sum), so that the pair label equals TC_EXACT's
+int rd_pair_none_refine(rd_handle* h, const uint8_t* const d_seq[2], const int64_t* const d_off[2], int64_t n, int max_len,
+                        int semantics, int precision, float* const d_logits[2], cudaStream_t st, int ostride = 1);
 int rd_launch_tail(rd_handle* h, const float* d_logits, int64_t n, float* d_probs, int8_t* d_labels,
                    int64_t* d_counts, cudaStream_t st);
 int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n, int mode,

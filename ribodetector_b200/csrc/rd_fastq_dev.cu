@@ -852,6 +852,13 @@ static int fastx_submit(rd_handle* h, int format, int slot, int ends, const uint
                                     s->d_logits[e], nullptr, nullptr, nullptr, h->s_cmp, 8);
             if (rc) return rc;
         }
+        if (mode == RD_PAIR_NONE) {
+            const uint8_t* sq[2] = {s->d_buf[slot][0], s->d_buf[slot][1]};
+            const int64_t* of[2] = {s->d_rec[slot][0] + 2, s->d_rec[slot][1] + 2};
+            float* lg[2] = {s->d_logits[0], s->d_logits[1]};
+            rc = rd_pair_none_refine(h, sq, of, n, max_len, semantics, precision, lg, h->s_cmp, 8);
+            if (rc) return rc;
+        }
         rc = rd_launch_pair(h, s->d_logits[0], s->d_logits[1], n, mode, s->d_labels[slot], s->d_res[slot] + 6, h->s_cmp);
         if (rc) return rc;
     }

@@ -111,18 +111,21 @@ reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [128][512]
 
 // ---- TC_AUTO: order-preserving compaction of the slots whose fast-pass margin is inside the band -------------
 // (slots are sorted by step count; keeping their order keeps the compacted tiles length-bucketed)
-__device__ __forceinline__ bool in_band(const int32_t* perm, const float2* logits, int64_t s, float tau) {
+// (mate != NULL: the band is on the SUMMED margin of a read and its mate, the quantity RD_PAIR_NONE decides on)
+__device__ __forceinline__ bool in_band(const int32_t* perm, const float2* logits, const float2* mate, int64_t s, float tau) {
     const int32_t rd = perm[s];
     if (rd < 0) return false;
     const float2 l = logits[rd];
-    return fabsf(l.y - l.x) < tau;                        // NaN (invalid read) compares false
+    float m = l.y - l.x;
+    if (mate) { const float2 o = mate[rd]; m += o.y - o.x; }
+    return fabsf(m) < tau;                                // NaN (invalid read) compares false
 }
 
 __global__ void __launch_bounds__(256)
-band_count_kernel(const int32_t* __restrict__ perm, const float2* __restrict__ logits, int64_t slots, float tau,
-                  int64_t* __restrict__ band) {
+band_count_kernel(const int32_t* __restrict__ perm, const float2* __restrict__ logits, const float2* __restrict__ mate,
+                  int64_t slots, float tau, int64_t* __restrict__ band) {
     const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const bool f = s < slots && in_band(perm, logits, s, tau);
+    const bool f = s < slots && in_band(perm, logits, mate, s, tau);
     const int c = __syncthreads_count(f);
     if (threadIdx.x == 0) band[blockIdx.x] = c;
 }
@@ -159,11 +162,11 @@ band_scan_kernel(int64_t* __restrict__ band, int64_t nb, int32_t* __restrict__ p
 
 __global__ void __launch_bounds__(256)
 band_write_kernel(const int32_t* __restrict__ perm, const uint32_t* __restrict__ splan, const float2* __restrict__ logits,
-                  int64_t slots, float tau, const int64_t* __restrict__ band, int32_t* __restrict__ perm2,
-                  uint32_t* __restrict__ splan2) {
+                  const float2* __restrict__ mate, int64_t slots, float tau, const int64_t* __restrict__ band,
+                  int32_t* __restrict__ perm2, uint32_t* __restrict__ splan2) {
     __shared__ int warp_cnt[8];
     const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const bool f = s < slots && in_band(perm, logits, s, tau);
+    const bool f = s < slots && in_band(perm, logits, mate, s, tau);
     const unsigned m = __ballot_sync(0xffffffffu, f);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) warp_cnt[w] = __popc(m);
@@ -177,13 +180,15 @@ band_write_kernel(const int32_t* __restrict__ perm, const uint32_t* __restrict__
     }
 }
 
-int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st) {
+int rd_launch_band_select(rd_handle* h, const float* d_logits, int64_t n_tiles, float tau, cudaStream_t st,
+                          const float* d_mate_logits) {
     const int64_t slots = n_tiles * RD_TILE;
     const int64_t nb = (slots + 255) / 256;
     const float2* lg = reinterpret_cast<const float2*>(d_logits);
-    band_count_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, lg, slots, tau, h->d_band);
+    const float2* mt = reinterpret_cast<const float2*>(d_mate_logits);
+    band_count_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, lg, mt, slots, tau, h->d_band);
     band_scan_kernel<<<1, 1024, 0, st>>>(h->d_band, nb, h->d_perm2, h->d_splan2);
-    band_write_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, h->d_splan, lg, slots, tau, h->d_band, h->d_perm2, h->d_splan2);
+    band_write_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_perm, h->d_splan, lg, mt, slots, tau, h->d_band, h->d_perm2, h->d_splan2);
     h->launches += 3;
     RD_CUDA(h, cudaGetLastError());
     return RD_OK;

@@ -512,6 +512,40 @@ def test_two_pass_modes_labels_equal_tc_exact(gpu_model, mode):
     assert int(r["counts"].sum()) == n
 
 
+@pytest.mark.parametrize("mode", ["tc_mixed", "tc_auto"])
+def test_pair_mode_none_labels_equal_tc_exact_on_adversarial_pairs(gpu_model, mode):
+    """`-e none` (the reference's default for pairs) takes the argmax of the SUM of the two ends' logits
+    (detect.py:655-661).  Pairs are built so that the sum is nearly zero while each end is far from its own band —
+    an rRNA-like read with a non-rRNA read of almost opposite margin — which is where a per-read band alone would let
+    first-pass errors decide; the host forms re-run such pairs in tc_exact (rd_pair_none_refine)."""
+    n = 1 << 19
+    seq, off = synth.synth_reads_fixed(n, 100, synth.SEED_BASE + 91)
+    ex = gpu_model.classify(seq, off, 100, precision="tc_exact")[0].cpu().numpy().astype(np.float64)
+    m = ex[:, 1] - ex[:, 0]
+    pos = np.flatnonzero(m > 0.5)
+    neg = np.flatnonzero(m < -0.5)
+    neg = neg[np.argsort(-m[neg])]                          # ascending |margin|
+    j = np.clip(np.searchsorted(-m[neg], m[pos]), 0, len(neg) - 1)
+    a, b = pos, neg[j]                                      # |m[a] + m[b]| is tiny
+    assert len(a) > 5000 and np.median(np.abs(m[a] + m[b])) < 5e-3
+    rows = seq.reshape(n, 100)
+    s1, s2 = rows[a].reshape(-1), rows[b].reshape(-1)
+    o = np.arange(len(a) + 1, dtype=np.int64) * 100
+    want = gpu_model.classify_pairs_host(s1, o, s2, o, 100, mode="none", precision="tc_exact", want_logits=True)
+    got = gpu_model.classify_pairs_host(s1, o, s2, o, 100, mode="none", precision=mode, want_logits=True)
+    sum_exact = (want["logits1"].numpy().astype(np.float64) + want["logits2"].numpy().astype(np.float64))
+    decided = np.abs(sum_exact[:, 1] - sum_exact[:, 0]) > 8e-4          # outside tc_exact's own band (two ends)
+    same = got["labels"].numpy() == want["labels"].numpy()
+    print("%s: %d adversarial pairs, %d with |summed margin| < 1e-2, %d label differences (all inside 8e-4: %s)"
+          % (mode, len(a), int((np.abs(sum_exact[:, 1] - sum_exact[:, 0]) < 1e-2).sum()), int((~same).sum()), bool(same[decided].all())))
+    assert same[decided].all()
+    assert 0 < int(want["labels"].sum()) < len(a)           # both outcomes occur
+    # the re-run pairs carry exact-grade logits on both ends
+    near = np.abs(sum_exact[:, 1] - sum_exact[:, 0]) < 0.02
+    assert np.array_equal(got["logits1"].numpy()[near], want["logits1"].numpy()[near])
+    assert np.array_equal(got["logits2"].numpy()[near], want["logits2"].numpy()[near])
+
+
 def test_cli_fasta_input_is_uppercased_joined_and_classified(gpu_model, numpy_oracle, tmp_path):
     """FASTA: the reference parser upper-cases and joins the sequence lines (fastx_parser.py:39-55), so lower-case
     bases ARE classified (unlike FASTQ, where they encode as zero rows) and records come out as 2 lines."""
