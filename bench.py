@@ -364,6 +364,18 @@ def run_strong(R):
     P, L = args.strong_pairs, READ_LEN
     if P <= 0:
         return None
+    # the shared source needs 2 * P * L bytes of /dev/shm: shrink the set (every rank takes the same decision) if the box
+    # has less, skip the block if it has next to none
+    import shutil
+    try:
+        free = shutil.disk_usage("/dev/shm").free if rank == 0 else 0
+    except OSError:
+        free = 0
+    (free,) = R.max_over_ranks(float(free))
+    fit = int((free - (1 << 30)) // (2 * L))
+    if fit < (1 << 20):
+        return {"skipped": "less than %.1f GB free in /dev/shm for the shared source buffer" % ((2 * L * (1 << 20) + (1 << 30)) / 1e9)} if rank == 0 else None
+    P = min(P, fit)
     nbytes = P * L
     tag = "rd_b200_strong_%s" % os.environ.get("MASTER_PORT", str(os.getpid()))
     paths = [os.path.join("/dev/shm", "%s_r%d.npy" % (tag, e)) for e in (1, 2)]
@@ -570,10 +582,19 @@ def run_ours(args, rank, world, local_rank):
     parity_fp32 = parity_block(got_par, ref32, args.precision, vs="the on-device fp32 CUDA-core kernel (packed semantics) on the "
                                "first %d reads of the timed batch" % n_par)
 
+    def guarded(name, fn):
+        """the extra blocks must not cost the headline line: an exception is reported in the block's place"""
+        try:
+            return fn()
+        except Exception as ex:             # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            return {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     log("configs C3/C4/C5")
-    configs = run_configs(R, pin) if not args.no_configs else None
+    configs = guarded("configs", lambda: run_configs(R, pin)) if not args.no_configs else None
     log("strong (fixed single-source set)")
-    strong = run_strong(R) if not args.no_strong else None
+    strong = guarded("strong", lambda: run_strong(R)) if not args.no_strong else None
     log("GPU phases done")
 
     if rank == 0:

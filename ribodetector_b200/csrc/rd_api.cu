@@ -237,8 +237,10 @@ extern "C" int rd_get_timing(rd_handle* h, double* ms4, int64_t* count4, int res
 }
 
 static float band_tau(int precision, int max_len) {
+    // the largest first-pass margin error over 2^20 reads per length grows like the square of the length for both
+    // first-pass kernels (profiles/r2_prec_err_big*.txt: fast 0.055 / 0.11 / 0.96, mixed 0.0033 / 0.009 / 0.14 at 100 / 150 / 300 bp)
     const float len_scale = max_len > 100 ? (float)max_len / 100.0f : 1.0f;
-    return precision == RD_PREC_TC_AUTO ? RD_BAND_FAST * len_scale : RD_BAND_MIXED * len_scale * len_scale;
+    return (precision == RD_PREC_TC_AUTO ? RD_BAND_FAST : RD_BAND_MIXED) * len_scale * len_scale;
 }
 
 int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
@@ -265,8 +267,6 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
             // first pass is inside a band several times the first pass's error bound (their slots are compacted on the
             // device and their count stays there, so nothing synchronises with the host): LABELS equal TC_EXACT's
             const bool fast = precision == RD_PREC_TC_AUTO;
-            // (the error of a recurrence grows with its length: linearly for the fast mode's bound, and the largest margin
-            //  error of the mixed kernel over 2^20 reads per length grows like the square: profiles/r2_prec_err_big.txt)
             const float tau = band_tau(precision, max_len);
             rc = ensure_band(h);
             if (!rc) rc = rd_launch_lstm_tc(h, d_seq, d_off, tiles, max_len, fast ? RD_PREC_TC_FAST : RD_PREC_TC_MIXED_RAW, d_logits, st,
