@@ -26,7 +26,7 @@ def timed(fn, reps=3):
 
 
 def main():
-    prec = sys.argv[1] if len(sys.argv) > 1 else "tc_exact"
+    prec = sys.argv[1] if len(sys.argv) > 1 else "tc_mixed"
     m = SeqModel(precision=prec)
     m.load_state_dict(load_weights())
     m.to("cuda:0")
