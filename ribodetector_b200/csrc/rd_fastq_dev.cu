@@ -206,19 +206,20 @@ fa_line_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk, co
                unsigned long long* __restrict__ line_desc, int64_t cap, int64_t* __restrict__ info) {
     int64_t n_nl; bool fin;
     const int64_t n_lines = fa_lines(buf, len, final_chunk, cap, info, &n_nl, &fin);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_lines) return;
-    int64_t b = i == 0 ? 0 : (int64_t)(line_end[i - 1] & LE_POS) + 1;
-    int64_t x = i < n_nl ? (int64_t)(line_end[i] & LE_POS) : len;
-    while (x > b && py_space(buf[x - 1])) --x;                              // line.strip()
-    while (b < x && py_space(buf[b])) ++b;
-    unsigned long long d = (unsigned long long)b;
-    if (x > b) {
-        if (x - b >= ((int64_t)1 << FA_LEN_BITS)) atomicMin(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)(i * 4 + 2));
-        d |= (unsigned long long)(x - b) << 40;
-        d |= buf[b] == '>' ? FA_HDR : FA_SEQ;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;                 // grid-stride: the grid is fixed
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += stride) {
+        int64_t b = i == 0 ? 0 : (int64_t)(line_end[i - 1] & LE_POS) + 1;
+        int64_t x = i < n_nl ? (int64_t)(line_end[i] & LE_POS) : len;
+        while (x > b && py_space(buf[x - 1])) --x;                          // line.strip()
+        while (b < x && py_space(buf[b])) ++b;
+        unsigned long long d = (unsigned long long)b;
+        if (x > b) {
+            if (x - b >= ((int64_t)1 << FA_LEN_BITS)) atomicMin(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)(i * 4 + 2));
+            d |= (unsigned long long)(x - b) << 40;
+            d |= buf[b] == '>' ? FA_HDR : FA_SEQ;
+        }
+        line_desc[i] = d;
     }
-    line_desc[i] = d;
 }
 
 __device__ __forceinline__ int fa_len(unsigned long long d) { return (int)((d >> 40) & ((1u << FA_LEN_BITS) - 1)); }
@@ -362,19 +363,20 @@ fa_emit_kernel(const uint8_t* __restrict__ buf, int64_t len, int final_chunk_in,
 __global__ void __launch_bounds__(256)
 fa_copy_kernel(uint8_t* __restrict__ buf, const unsigned long long* __restrict__ line_desc, const int64_t* __restrict__ seq_at,
                const int64_t* __restrict__ info, int64_t seq_base, int64_t seq_limit) {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const int hl = threadIdx.x & 15;
-    if (i >= info[6]) return;
-    const unsigned long long d = line_desc[i];
-    if (!(d & FA_SEQ)) return;
-    const int64_t b = (int64_t)(d & ((1ull << 40) - 1));
-    const int l = fa_len(d);
-    const int64_t dst = seq_at[i];
-    if (dst + l > seq_limit) return;                                        // (cannot happen: the region is as large as the text)
-    uint8_t* o = buf + seq_base + dst;
-    for (int j = hl; j < l; j += 16) {
-        const uint8_t c = buf[b + j];
-        o[j] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c;              // .upper()
+    const int64_t n_lines = info[6], stride = ((int64_t)gridDim.x * blockDim.x) >> 4;      // grid-stride: the grid is fixed
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < n_lines; i += stride) {
+        const unsigned long long d = line_desc[i];
+        if (!(d & FA_SEQ)) continue;
+        const int64_t b = (int64_t)(d & ((1ull << 40) - 1));
+        const int l = fa_len(d);
+        const int64_t dst = seq_at[i];
+        if (dst + l > seq_limit) continue;                                  // (cannot happen: the region is as large as the text)
+        uint8_t* o = buf + seq_base + dst;
+        for (int j = hl; j < l; j += 16) {
+            const uint8_t c = buf[b + j];
+            o[j] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c;          // .upper()
+        }
     }
 }
 
@@ -680,12 +682,12 @@ static int launch_scan_fasta(rd_handle* h, rd_fq_state* s, int e, uint8_t* d_buf
                                                                      s->d_line_end[e], cap, d_info);
         h->launches += 1;
     }
-    fa_line_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, len, final_chunk, s->d_line_end[e], s->d_line_desc[e], cap, d_info);
+    fa_line_kernel<<<(unsigned)std::min<int64_t>(nblk, (int64_t)h->sm_count * 8), 256, 0, st>>>(d_buf, len, final_chunk, s->d_line_end[e], s->d_line_desc[e], cap, d_info);
     fa_sum_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, len, final_chunk, cap, d_info, s->d_line_desc[e], s->d_fa_blocksum);
     fa_scan_kernel<<<1, 1024, 0, st>>>(d_buf, len, final_chunk, cap, s->d_fa_blocksum, nblk, max_records, d_info);
     fa_emit_kernel<<<(unsigned)nblk, 256, 0, st>>>(d_buf, len, final_chunk, cap, s->d_line_desc[e], s->d_line_end[e],
                                                    s->d_fa_blocksum, seq_base, d_rec, max_records, s->d_seq_at[e], d_info);
-    fa_copy_kernel<<<(unsigned)((cap * 16 + 255) / 256), 256, 0, st>>>(d_buf, s->d_line_desc[e], s->d_seq_at[e], d_info, seq_base, len);
+    fa_copy_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, st>>>(d_buf, s->d_line_desc[e], s->d_seq_at[e], d_info, seq_base, len);
     h->launches += 5;
     RD_CUDA(h, cudaGetLastError());
     return RD_OK;
