@@ -108,8 +108,11 @@ int rd_abi_version(void);
  * (model/model.py:11-29, detect.py:93,115-119).  All weight pointers are HOST fp32 arrays in
  * the reference state_dict layout: w_ih [4H,4], w_hh [4H,H], b_ih [4H], b_hh [4H] (gate row
  * order i,f,g,o) for the forward ("_l0") and reverse ("_l0_reverse") directions, w_out [2,2H],
- * b_out [2].  hidden must be 128.  Uploads the weights, builds the gate-input table, the
- * tensor-core weight images and the reverse-direction logit LUT on `device`. */
+ * b_out [2].  hidden = 128 (the shipped checkpoint) runs on the tensor-core kernels; any other
+ * multiple of 32 between 32 and 256 is accepted (the reference's SeqModel takes any hidden_size)
+ * and runs every RD_PREC_* on the generic fp32 CUDA-core kernel; anything else returns
+ * RD_ERR_UNSUPPORTED.  Uploads the weights, builds the gate-input table, the tensor-core weight
+ * images (H = 128) and the reverse-direction logit LUT on `device`. */
 int rd_create(int device,
               const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
               const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r,

@@ -70,7 +70,9 @@ extern "C" int rd_create(int device,
                          const float* w_out, const float* b_out, int hidden, rd_handle** out) {
     if (!out) return fail(nullptr, RD_ERR_INVALID, "rd_create: out is NULL");
     *out = nullptr;
-    if (hidden != RD_H) return fail(nullptr, RD_ERR_UNSUPPORTED, "rd_create: kernels are built for hidden_size 128");
+    if (hidden < 32 || hidden > 256 || hidden % 32 != 0)
+        return fail(nullptr, RD_ERR_UNSUPPORTED, "rd_create: hidden_size must be a multiple of 32 between 32 and 256 "
+                                                 "(128 runs on the tensor-core kernels, the others on the generic fp32 kernel)");
     if (!w_ih_f || !w_hh_f || !b_ih_f || !b_hh_f || !w_ih_r || !w_hh_r || !b_ih_r || !b_hh_r || !w_out || !b_out)
         return fail(nullptr, RD_ERR_INVALID, "rd_create: NULL weight pointer");
     int ndev = 0;
@@ -82,6 +84,8 @@ extern "C" int rd_create(int device,
     rd_handle* h = new (std::nothrow) rd_handle();
     if (!h) return fail(nullptr, RD_ERR_NOMEM, "rd_create: out of host memory");
     h->device = device;
+    h->hidden = hidden;
+    const int H = hidden, G4 = 4 * hidden;
     auto bail = [&](int code) { g_create_err = h->err; rd_destroy(h); return code; };
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(_e); return bail(RD_ERR_CUDA); } } while (0)
     CK(cudaSetDevice(device));
@@ -90,34 +94,34 @@ extern "C" int rd_create(int device,
     h->sm_count = prop.multiProcessorCount;
 
     // gate-input tables: row c<4 = W_ih[:,c] + b_ih + b_hh ; row 4 = b_ih + b_hh   (x_t is one-hot or zero)
-    std::vector<float> tab_f(5 * RD_G4), tab_r(5 * RD_G4), whh_t(RD_H * RD_G4), whh_r_t(RD_H * RD_G4);
+    std::vector<float> tab_f(5 * G4), tab_r(5 * G4), whh_t(H * G4), whh_r_t(H * G4);
     for (int code = 0; code < 5; ++code)
-        for (int j = 0; j < RD_G4; ++j) {
+        for (int j = 0; j < G4; ++j) {
             float bf = b_ih_f[j] + b_hh_f[j], br = b_ih_r[j] + b_hh_r[j];
-            tab_f[code * RD_G4 + j] = code < 4 ? w_ih_f[j * 4 + code] + bf : bf;
-            tab_r[code * RD_G4 + j] = code < 4 ? w_ih_r[j * 4 + code] + br : br;
+            tab_f[code * G4 + j] = code < 4 ? w_ih_f[j * 4 + code] + bf : bf;
+            tab_r[code * G4 + j] = code < 4 ? w_ih_r[j * 4 + code] + br : br;
         }
-    for (int j = 0; j < RD_G4; ++j)
-        for (int k = 0; k < RD_H; ++k) {
-            whh_t[k * RD_G4 + j] = w_hh_f[j * RD_H + k];
-            whh_r_t[k * RD_G4 + j] = w_hh_r[j * RD_H + k];
+    for (int j = 0; j < G4; ++j)
+        for (int k = 0; k < H; ++k) {
+            whh_t[k * G4 + j] = w_hh_f[j * H + k];
+            whh_r_t[k * G4 + j] = w_hh_r[j * H + k];
         }
-    CK(cudaMalloc(&h->d_tab_f, sizeof(float) * 5 * RD_G4));
-    CK(cudaMalloc(&h->d_tab_r, sizeof(float) * 5 * RD_G4));
-    CK(cudaMalloc(&h->d_whh_t, sizeof(float) * RD_H * RD_G4));
-    CK(cudaMalloc(&h->d_whh_r_t, sizeof(float) * RD_H * RD_G4));
-    CK(cudaMalloc(&h->d_wout, sizeof(float) * 2 * 2 * RD_H));
+    CK(cudaMalloc(&h->d_tab_f, sizeof(float) * 5 * G4));
+    CK(cudaMalloc(&h->d_tab_r, sizeof(float) * 5 * G4));
+    CK(cudaMalloc(&h->d_whh_t, sizeof(float) * H * G4));
+    CK(cudaMalloc(&h->d_whh_r_t, sizeof(float) * H * G4));
+    CK(cudaMalloc(&h->d_wout, sizeof(float) * 2 * 2 * H));
     CK(cudaMalloc(&h->d_bout, sizeof(float) * 2));
     CK(cudaMalloc(&h->d_revlut, sizeof(float) * RD_MAX_LEN * 5 * 2));
-    CK(cudaMalloc(&h->d_lutstate, sizeof(double) * 2 * RD_H));
+    CK(cudaMalloc(&h->d_lutstate, sizeof(double) * 2 * H));
     CK(cudaMalloc(&h->d_hist, sizeof(int32_t) * (RD_MAX_LEN + 2)));
     CK(cudaMalloc(&h->d_cursor, sizeof(int32_t) * (RD_MAX_LEN + 2)));
     CK(cudaMalloc(&h->d_ctrl, sizeof(int32_t) * 8));
-    CK(cudaMemcpy(h->d_tab_f, tab_f.data(), sizeof(float) * 5 * RD_G4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_tab_r, tab_r.data(), sizeof(float) * 5 * RD_G4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_whh_t, whh_t.data(), sizeof(float) * RD_H * RD_G4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_whh_r_t, whh_r_t.data(), sizeof(float) * RD_H * RD_G4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_wout, w_out, sizeof(float) * 2 * 2 * RD_H, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_tab_f, tab_f.data(), sizeof(float) * 5 * G4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_tab_r, tab_r.data(), sizeof(float) * 5 * G4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_whh_t, whh_t.data(), sizeof(float) * H * G4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_whh_r_t, whh_r_t.data(), sizeof(float) * H * G4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_wout, w_out, sizeof(float) * 2 * 2 * H, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_bout, b_out, sizeof(float) * 2, cudaMemcpyHostToDevice));
     CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
@@ -130,8 +134,10 @@ extern "C" int rd_create(int device,
     CK(cudaMalloc(&h->d_stage_counts, sizeof(int64_t) * 4));
     int rc = rd_build_reverse_lut(h, 512, 0);
     if (rc != RD_OK) return bail(rc);
-    rc = rd_tc_create(h, w_hh_f, w_ih_f, b_ih_f, b_hh_f);
-    if (rc != RD_OK) return bail(rc);
+    if (hidden == RD_H) {                          // tensor-core weight images (the kernels are laid out for H = 128)
+        rc = rd_tc_create(h, w_hh_f, w_ih_f, b_ih_f, b_hh_f);
+        if (rc != RD_OK) return bail(rc);
+    }
     CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;
@@ -246,7 +252,8 @@ static float band_tau(int precision, int max_len) {
 int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                            int semantics, int precision, float* d_logits, float* d_probs,
                            int8_t* d_labels, int64_t* d_counts, cudaStream_t st, int ostride) {
-    const bool need_codes = precision == RD_PREC_FP32;
+    const bool generic = h->hidden != RD_H;        // another hidden size: every precision runs the generic fp32 kernel
+    const bool need_codes = precision == RD_PREC_FP32 && !generic;
     int rc = ensure_scratch(h, n, max_len, need_codes);
     if (rc) return rc;
     if (semantics == RD_SEM_PADDED && max_len > h->lut_rows) {      // krev < max_len: extend the reverse-direction table
@@ -261,7 +268,8 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
     if (rc) return rc;
     {
         StageTimer tm(h, 1, st);
-        if (precision == RD_PREC_FP32) rc = rd_launch_lstm_simt(h, tiles, max_len, d_logits, st);
+        if (generic) rc = rd_launch_lstm_generic(h, d_seq, d_off, tiles, max_len, d_logits, st, ostride);
+        else if (precision == RD_PREC_FP32) rc = rd_launch_lstm_simt(h, tiles, max_len, d_logits, st);
         else if (precision == RD_PREC_TC_AUTO || precision == RD_PREC_TC_MIXED) {
             // two passes: the cheaper kernel over everything, then the exact kernel over the reads whose margin from the
             // first pass is inside a band several times the first pass's error bound (their slots are compacted on the
@@ -287,7 +295,7 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
 
 int rd_pair_none_refine(rd_handle* h, const uint8_t* const d_seq[2], const int64_t* const d_off[2], int64_t n, int max_len,
                         int semantics, int precision, float* const d_logits[2], cudaStream_t st, int ostride) {
-    if (n == 0 || (precision != RD_PREC_TC_AUTO && precision != RD_PREC_TC_MIXED)) return RD_OK;
+    if (n == 0 || h->hidden != RD_H || (precision != RD_PREC_TC_AUTO && precision != RD_PREC_TC_MIXED)) return RD_OK;
     const float tau = 2.0f * band_tau(precision, max_len);          // two first-pass margins add up
     int rc = ensure_band(h);
     for (int e = 0; e < 2 && !rc; ++e) {
@@ -402,7 +410,7 @@ static int classify_host_impl(rd_handle* h, int ends,
             max_bytes = std::max(max_bytes, off[e][cut[c + 1]] - off[e][cut[c]]);
     rc = ensure_stage(h, chunk, max_bytes, ends, probs != nullptr);
     if (rc) return rc;
-    rc = ensure_scratch(h, chunk, max_len, precision == RD_PREC_FP32);
+    rc = ensure_scratch(h, chunk, max_len, precision == RD_PREC_FP32 && h->hidden == RD_H);
     if (rc) return rc;
     RD_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(int64_t) * 4, h->s_cmp));
 

@@ -46,6 +46,10 @@ __device__ __forceinline__ uint32_t rd_base_code(uint32_t b) {
 struct rd_handle {
     int device = 0;
     int sm_count = 0;
+    int hidden = RD_H;             // hidden size of the loaded model; the tensor-core and tuned fp32 kernels need RD_H,
+                                   // any other multiple of 32 up to 256 runs on the generic fp32 kernel (rd_lstm_generic.cu)
+    bool generic_attr_set = false, lut_attr_set = false;
+    int generic_ctas_per_sm = 1;
     std::string err;
     int64_t launches = 0;
 
@@ -118,6 +122,8 @@ int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int
 int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                      int layout, float* d_out, int64_t* d_row_off, cudaStream_t st);
 int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int max_len, float* d_logits, cudaStream_t st);
+int rd_launch_lstm_generic(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
+                           float* d_logits, cudaStream_t st, int ostride = 1);
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
                       int precision, float* d_logits, cudaStream_t st, const uint32_t* d_splan = nullptr,
                       const int32_t* d_perm = nullptr, const int64_t* d_n_reads = nullptr, int ostride = 1);

@@ -64,35 +64,39 @@ pair_kernel(const float2* __restrict__ l1, const float2* __restrict__ l2, int64_
 // the reverse LSTM has consumed k zero-input steps (k = 0 under packed semantics) plus one
 // base: its hidden state is a function of (k, code) only.  Computed once in fp64 and folded
 // through W_out[:, H:2H] into logit offsets lut[k][code][2].   
-__global__ void __launch_bounds__(RD_G4, 1)
-reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [128][512]
-                   const float* __restrict__ tab_r,    // [5][512]
-                   const float* __restrict__ wout,     // [2][256]
-                   int k0, int k1, double* __restrict__ state,   // rows [k0, k1); state = (h, c) after k0 zero steps
+__global__ void __launch_bounds__(1024, 1)
+reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [H][4H]
+                   const float* __restrict__ tab_r,    // [5][4H]
+                   const float* __restrict__ wout,     // [2][2H]
+                   int H, int k0, int k1, double* __restrict__ state,   // rows [k0, k1); state = (h, c) after k0 zero steps
                    float* __restrict__ lut) {
-    __shared__ double h[RD_H], c[RD_H];
-    __shared__ double z[5][RD_G4];
-    __shared__ double hrev[5][RD_H];
-    const int j = threadIdx.x;                       // gate row
-    if (j < RD_H) { h[j] = k0 ? state[j] : 0.0; c[j] = k0 ? state[RD_H + j] : 0.0; }
+    extern __shared__ double lut_sm[];                // h[H] | c[H] | z[5][4H] | hrev[5][H]
+    const int G4 = 4 * H;
+    double* h = lut_sm;
+    double* c = h + H;
+    double* z = c + H;
+    double* hrev = z + 5 * G4;
+    const int j = threadIdx.x;                       // gate row (blockDim.x = 4H)
+    if (j < H) { h[j] = k0 ? state[j] : 0.0; c[j] = k0 ? state[H + j] : 0.0; }
     __syncthreads();
     for (int k = k0; k < k1; ++k) {
         double dot = 0.0;
-        for (int m = 0; m < RD_H; ++m) dot += (double)whh_r_t[m * RD_G4 + j] * h[m];
+        for (int m = 0; m < H; ++m) dot += (double)whh_r_t[m * G4 + j] * h[m];
 #pragma unroll
-        for (int code = 0; code < 5; ++code) z[code][j] = dot + (double)tab_r[code * RD_G4 + j];
+        for (int code = 0; code < 5; ++code) z[code * G4 + j] = dot + (double)tab_r[code * G4 + j];
         __syncthreads();
         double c_next = 0.0, h_next = 0.0;
-        if (j < RD_H) {
+        if (j < H) {
 #pragma unroll
             for (int code = 0; code < 5; ++code) {
-                double ig = 1.0 / (1.0 + exp(-z[code][j]));
-                double fg = 1.0 / (1.0 + exp(-z[code][RD_H + j]));
-                double gg = tanh(z[code][2 * RD_H + j]);
-                double og = 1.0 / (1.0 + exp(-z[code][3 * RD_H + j]));
+                const double* zc = z + code * G4;
+                double ig = 1.0 / (1.0 + exp(-zc[j]));
+                double fg = 1.0 / (1.0 + exp(-zc[H + j]));
+                double gg = tanh(zc[2 * H + j]);
+                double og = 1.0 / (1.0 + exp(-zc[3 * H + j]));
                 double cc = fg * c[j] + ig * gg;
                 double hh = og * tanh(cc);
-                hrev[code][j] = hh;
+                hrev[code * H + j] = hh;
                 if (code == 4) { c_next = cc; h_next = hh; }
             }
         }
@@ -100,13 +104,13 @@ reverse_lut_kernel(const float* __restrict__ whh_r_t,  // [128][512]
         if (j < 10) {                                 // 5 codes x 2 classes
             int code = j >> 1, cls = j & 1;
             double s = 0.0;
-            for (int u = 0; u < RD_H; ++u) s += (double)wout[cls * 2 * RD_H + RD_H + u] * hrev[code][u];
+            for (int u = 0; u < H; ++u) s += (double)wout[cls * 2 * H + H + u] * hrev[code * H + u];
             lut[((int64_t)k * 5 + code) * 2 + cls] = (float)s;
         }
-        if (j < RD_H) { h[j] = h_next; c[j] = c_next; }
+        if (j < H) { h[j] = h_next; c[j] = c_next; }
         __syncthreads();
     }
-    if (j < RD_H) { state[j] = h[j]; state[RD_H + j] = c[j]; }       // the chain resumes here when the table is extended
+    if (j < H) { state[j] = h[j]; state[H + j] = c[j]; }       // the chain resumes here when the table is extended
 }
 
 // ---- TC_AUTO: order-preserving compaction of the slots whose fast-pass margin is inside the band -------------
@@ -221,7 +225,13 @@ int rd_launch_pair(rd_handle* h, const float* d_l1, const float* d_l2, int64_t n
 int rd_build_reverse_lut(rd_handle* h, int rows, cudaStream_t st) {
     if (rows > RD_MAX_LEN) rows = RD_MAX_LEN;
     if (rows <= h->lut_rows) return RD_OK;
-    reverse_lut_kernel<<<1, RD_G4, 0, st>>>(h->d_whh_r_t, h->d_tab_r, h->d_wout, h->lut_rows, rows, h->d_lutstate, h->d_revlut);
+    const int H = h->hidden;
+    const size_t smem = sizeof(double) * (size_t)(27 * H);           // h, c, z[5][4H], hrev[5][H]
+    if (!h->lut_attr_set) {
+        RD_CUDA(h, cudaFuncSetAttribute(reverse_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->lut_attr_set = true;
+    }
+    reverse_lut_kernel<<<1, 4 * H, smem, st>>>(h->d_whh_r_t, h->d_tab_r, h->d_wout, H, h->lut_rows, rows, h->d_lutstate, h->d_revlut);
     h->launches += 1;
     h->lut_rows = rows;
     RD_CUDA(h, cudaGetLastError());

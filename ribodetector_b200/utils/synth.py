@@ -80,3 +80,19 @@ def fastq_text(n, length, seed, n_frac=0.001):
     rec[:, 15 + length:15 + 2 * length] = ord("I")
     rec[:, 15 + 2 * length] = ord("\n")
     return rec.reshape(-1)
+
+
+def synth_weights(hidden_size, seed, gain=3.5):
+    """A seeded random checkpoint of the reference architecture at another hidden size (state_dict keys of
+    ``model/model.py:16-24``): U(-g/sqrt(H), g/sqrt(H)) like ``nn.LSTM``'s default init, times `gain` so that gates
+    leave the linear range.  Used by oracle/gen_golden_arch.py and by the tests of the generic-H kernel — the
+    reference ships one checkpoint (H = 128) only."""
+    rng = np.random.Generator(np.random.PCG64([seed, hidden_size]))
+    H = hidden_size
+    a = gain / np.sqrt(H)
+    shapes = (("rnn.weight_ih_l0", (4 * H, 4)), ("rnn.weight_hh_l0", (4 * H, H)),
+              ("rnn.bias_ih_l0", (4 * H,)), ("rnn.bias_hh_l0", (4 * H,)),
+              ("rnn.weight_ih_l0_reverse", (4 * H, 4)), ("rnn.weight_hh_l0_reverse", (4 * H, H)),
+              ("rnn.bias_ih_l0_reverse", (4 * H,)), ("rnn.bias_hh_l0_reverse", (4 * H,)),
+              ("out.weight", (2, 2 * H)), ("out.bias", (2,)))
+    return {k: rng.uniform(-a, a, size=s).astype(np.float32) for k, s in shapes}

@@ -63,10 +63,15 @@ def test_create_without_gpu_fails_loudly(weights):
 
 def test_model_argument_validation(weights):
     from ribodetector_b200.model import SeqModel
-    with pytest.raises(ValueError):
-        SeqModel(4, 64, 1, 2)
+    for bad_h in (16, 100, 288, 0):        # hidden_size: multiples of 32 between 32 and 256
+        with pytest.raises(ValueError):
+            SeqModel(4, bad_h, 1, 2)
+    SeqModel(4, 64, 1, 2)
+    SeqModel(4, 256, 1, 2)
     with pytest.raises(ValueError):
         SeqModel(4, 128, 2, 2)
+    with pytest.raises(RuntimeError):
+        SeqModel(4, 64, 1, 2).load_state_dict(weights)      # a 128-unit checkpoint into a 64-unit model: size mismatch
     m = SeqModel(4, 128, 1, 2)
     bad = dict(weights)
     bad.pop("out.bias")

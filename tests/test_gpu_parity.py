@@ -623,3 +623,65 @@ def test_full_size_config3_pairs_per_gpu_periodic(gpu_model):
     assert np.array_equal(labels[0], one) and (labels == labels[0][None, :]).all()
     assert np.array_equal(r["counts"].numpy(), 12 * pairs.counts(one))
     assert int(r["counts"].sum()) == 12 * period
+
+
+# ---- hidden sizes other than the shipped 128 (SeqModel(**arch.args), model/model.py:11-29) ---------------------------
+def _arch_model(H, precision="fp32"):
+    from ribodetector_b200.model import SeqModel
+    g = load_golden("arch")
+    w = synth.synth_weights(H, int(g["weight_seed"]))
+    m = SeqModel(input_size=4, hidden_size=H, num_layers=1, num_classes=2, pack_seq=True, precision=precision)
+    m.load_state_dict(w)
+    return m.to("cuda:0").eval(), w, g
+
+
+@pytest.mark.parametrize("H", [32, 64, 96, 192, 256])
+@pytest.mark.parametrize("semantics", ["packed", "padded"])
+def test_other_hidden_sizes_match_reference_golden(H, semantics):
+    """The reference's own SeqModel / model_cpu.SeqModel instantiated at another hidden_size with seeded weights
+    (oracle/gen_golden_arch.py): fp32 bounds, every precision name (they all run the generic fp32 kernel)."""
+    m, _w, g = _arch_model(H)
+    try:
+        L = int(g["max_len"])
+        for prec in PRECISIONS:
+            logits, probs, labels = m.classify(g["seq"], g["off"], L, semantics=semantics, precision=prec, want_probs=True)
+            got = logits.cpu().numpy()
+            check_logits(got, g["logits_%s_h%d" % (semantics, H)], "fp32", L)
+            assert np.array_equal(labels.cpu().numpy(), pairs.argmax_labels(got))
+            assert np.abs(probs.cpu().numpy() - softmax2(got.astype(np.float64))).max() < 1e-6
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("H", [64, 256])
+def test_other_hidden_sizes_ragged_reads_host_api_and_pairs(H):
+    """Ragged 1..150 bp reads against the fp64 oracle built from the same seeded weights, through the device call, the host
+    pipeline and the pair entry point; odd group counts (n not a multiple of 16 or 128)."""
+    from oracle.model_numpy import NumpyOracle
+    m, w, _g = _arch_model(H)
+    try:
+        seq, off = synth.synth_reads(3001, 1, 150, 991 + H, n_frac=0.01)
+        reads = synth.to_strings(seq, off)
+        orc = NumpyOracle(w, np.float64)
+        for semantics in ("packed", "padded"):
+            want = orc.logits(reads, 120, semantics)
+            got = m.classify(seq, off, 120, semantics=semantics)[0].cpu().numpy()
+            check_logits(got, want, "fp32", 120)
+            r = m.classify_host(seq, off, 120, semantics=semantics)
+            lab = r["labels"].numpy()
+            assert np.array_equal(r["logits"].numpy(), got)
+            assert np.array_equal(lab, pairs.argmax_labels(got))
+            assert np.array_equal(r["counts"].numpy(), pairs.counts(lab))
+        n = 1500
+        s1, o1 = seq[: off[n]], off[: n + 1]
+        s2, o2 = seq[off[n]: off[2 * n]], off[n: 2 * n + 1] - off[n]
+        l1 = orc.logits(reads[:n], 120, "packed")
+        l2 = orc.logits(reads[n:2 * n], 120, "packed")
+        for mode in pairs.MODES:
+            lab = m.classify_pairs_host(s1, o1, s2, o2, 120, mode=mode)["labels"].numpy()
+            want = pairs.pair_labels(l1.astype(np.float32), l2.astype(np.float32), mode)
+            sure = (np.abs(l1[:, 1] - l1[:, 0]) > 1e-3) & (np.abs(l2[:, 1] - l2[:, 0]) > 1e-3) & \
+                   (np.abs((l1 + l2)[:, 1] - (l1 + l2)[:, 0]) > 1e-3)
+            assert np.array_equal(lab[sure], want[sure]), mode
+    finally:
+        m.close()
