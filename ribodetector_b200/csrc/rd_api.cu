@@ -377,10 +377,10 @@ __global__ void rebase_kernel(int64_t* off, int64_t n1, int64_t base) {
     if (i < n1) off[i] -= base;
 }
 
-static int classify_host_impl(rd_handle* h, int ends,
-                              const uint8_t* const seq[2], const int64_t* const off[2], int64_t n,
-                              int max_len, int semantics, int precision, int mode,
-                              float* const logits[2], float* probs, int8_t* labels, int64_t* counts) {
+static int classify_host_run(rd_handle* h, int ends,
+                             const uint8_t* const seq[2], const int64_t* const off[2], int64_t n,
+                             int max_len, int semantics, int precision, int mode,
+                             float* const logits[2], float* probs, int8_t* labels, int64_t* counts) {
     int rc = check_common(h, n, max_len, "rd_classify_host");
     if (rc) return rc;
     if (semantics != RD_SEM_PACKED && semantics != RD_SEM_PADDED)
@@ -487,6 +487,22 @@ static int classify_host_impl(rd_handle* h, int ends,
     RD_CUDA(h, cudaStreamSynchronize(h->s_out));
     if (counts) { counts[0] = cnt[0]; counts[1] = cnt[1]; counts[2] = cnt[2]; }
     return RD_OK;
+}
+
+// A call that fails half way has copies in flight from and into the CALLER's buffers: drain the device before the error
+// is returned, so that the caller may free or reuse them at once.
+static int classify_host_impl(rd_handle* h, int ends,
+                              const uint8_t* const seq[2], const int64_t* const off[2], int64_t n,
+                              int max_len, int semantics, int precision, int mode,
+                              float* const logits[2], float* probs, int8_t* labels, int64_t* counts) {
+    const int rc = classify_host_run(h, ends, seq, off, n, max_len, semantics, precision, mode, logits, probs, labels, counts);
+    if (rc != RD_OK && h && rc != RD_ERR_INVALID) {
+        const std::string msg = h->err;            // (keep the first error's message)
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        h->err = msg;
+    }
+    return rc;
 }
 
 extern "C" int rd_classify_host(rd_handle* h, const uint8_t* seq, const int64_t* off, int64_t n,
