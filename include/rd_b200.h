@@ -110,7 +110,7 @@ int rd_abi_version(void);
  * order i,f,g,o) for the forward ("_l0") and reverse ("_l0_reverse") directions, w_out [2,2H],
  * b_out [2].  hidden = 128 (the shipped checkpoint) runs on the tensor-core kernels; any other
  * multiple of 32 between 32 and 256 is accepted (the reference's SeqModel takes any hidden_size)
- * and runs every RD_PREC_* on the generic fp32 CUDA-core kernel; anything else returns
+ * and runs every RD_PREC_* on the fp32 CUDA-core kernel; anything else returns
  * RD_ERR_UNSUPPORTED.  Uploads the weights, builds the gate-input table, the tensor-core weight
  * images (H = 128) and the reverse-direction logit LUT on `device`. */
 int rd_create(int device,

@@ -22,11 +22,11 @@ extern "C" const char* rd_last_error(const rd_handle* h) {
 extern "C" int64_t rd_kernel_launches(const rd_handle* h) { return h ? h->launches : 0; }
 
 static void free_scratch(rd_handle* h) {
-    cudaFree(h->d_plan); cudaFree(h->d_splan); cudaFree(h->d_perm); cudaFree(h->d_codes);
+    cudaFree(h->d_plan); cudaFree(h->d_splan); cudaFree(h->d_perm);
     cudaFree(h->d_splan2); cudaFree(h->d_perm2); cudaFree(h->d_band);
-    h->d_plan = h->d_splan = nullptr; h->d_perm = nullptr; h->d_codes = nullptr;
+    h->d_plan = h->d_splan = nullptr; h->d_perm = nullptr;
     h->d_splan2 = nullptr; h->d_perm2 = nullptr; h->d_band = nullptr;
-    h->cap_n = h->cap_slots = h->cap_codes = h->cap_band = 0;
+    h->cap_n = h->cap_slots = h->cap_band = 0;
 }
 
 static int ensure_band(rd_handle* h) {          // TC_AUTO scratch, sized like the slot tables
@@ -41,19 +41,17 @@ static int ensure_band(rd_handle* h) {          // TC_AUTO scratch, sized like t
     return RD_OK;
 }
 
-static int ensure_scratch(rd_handle* h, int64_t n, int max_len, bool need_codes = false) {
+static int ensure_scratch(rd_handle* h, int64_t n) {
     int64_t tiles = (n + RD_TILE - 1) / RD_TILE;
     int64_t slots = (tiles + 1) * RD_TILE;                 // + one pad tile: the exact kernel works on tile pairs
-    int64_t codes = need_codes ? slots * (int64_t)max_len : 0;   // only the fp32 CUDA-core kernel wants the code buffer
-    if (n <= h->cap_n && slots <= h->cap_slots && codes <= h->cap_codes) return RD_OK;
+    if (n <= h->cap_n && slots <= h->cap_slots) return RD_OK;
     RD_CUDA(h, cudaDeviceSynchronize());
-    int64_t nn = std::max(n, h->cap_n), ss = std::max(slots, h->cap_slots), cc = std::max(codes, h->cap_codes);
+    int64_t nn = std::max(n, h->cap_n), ss = std::max(slots, h->cap_slots);
     free_scratch(h);
     RD_CUDA(h, cudaMalloc(&h->d_plan, sizeof(uint32_t) * std::max<int64_t>(nn, 1)));
     RD_CUDA(h, cudaMalloc(&h->d_splan, sizeof(uint32_t) * std::max<int64_t>(ss, 1)));
     RD_CUDA(h, cudaMalloc(&h->d_perm, sizeof(int32_t) * std::max<int64_t>(ss, 1)));
-    RD_CUDA(h, cudaMalloc(&h->d_codes, std::max<int64_t>(cc, 1)));
-    h->cap_n = nn; h->cap_slots = ss; h->cap_codes = cc;
+    h->cap_n = nn; h->cap_slots = ss;
     return RD_OK;
 }
 
@@ -61,7 +59,7 @@ extern "C" int rd_reserve(rd_handle* h, int64_t n, int max_len) {
     if (!h) return RD_ERR_INVALID;
     if (n < 0 || max_len < 1 || max_len > RD_MAX_LEN) return fail(h, RD_ERR_INVALID, "rd_reserve: bad n/max_len");
     RD_CUDA(h, cudaSetDevice(h->device));
-    return ensure_scratch(h, n, max_len);
+    return ensure_scratch(h, n);
 }
 
 extern "C" int rd_create(int device,
@@ -72,7 +70,7 @@ extern "C" int rd_create(int device,
     *out = nullptr;
     if (hidden < 32 || hidden > 256 || hidden % 32 != 0)
         return fail(nullptr, RD_ERR_UNSUPPORTED, "rd_create: hidden_size must be a multiple of 32 between 32 and 256 "
-                                                 "(128 runs on the tensor-core kernels, the others on the generic fp32 kernel)");
+                                                 "(128 runs on the tensor-core kernels, the others on the fp32 CUDA-core kernel)");
     if (!w_ih_f || !w_hh_f || !b_ih_f || !b_hh_f || !w_ih_r || !w_hh_r || !b_ih_r || !b_hh_r || !w_out || !b_out)
         return fail(nullptr, RD_ERR_INVALID, "rd_create: NULL weight pointer");
     int ndev = 0;
@@ -94,7 +92,7 @@ extern "C" int rd_create(int device,
     h->sm_count = prop.multiProcessorCount;
 
     // gate-input tables: row c<4 = W_ih[:,c] + b_ih + b_hh ; row 4 = b_ih + b_hh   (x_t is one-hot or zero)
-    std::vector<float> tab_f(5 * G4), tab_r(5 * G4), whh_t(H * G4), whh_r_t(H * G4);
+    std::vector<float> tab_f(5 * G4), tab_r(5 * G4), whh_r_t(H * G4);
     for (int code = 0; code < 5; ++code)
         for (int j = 0; j < G4; ++j) {
             float bf = b_ih_f[j] + b_hh_f[j], br = b_ih_r[j] + b_hh_r[j];
@@ -103,13 +101,19 @@ extern "C" int rd_create(int device,
         }
     for (int j = 0; j < G4; ++j)
         for (int k = 0; k < H; ++k) {
-            whh_t[k * G4 + j] = w_hh_f[j * H + k];
             whh_r_t[k * G4 + j] = w_hh_r[j * H + k];
         }
     CK(cudaMalloc(&h->d_tab_f, sizeof(float) * 5 * G4));
     CK(cudaMalloc(&h->d_tab_r, sizeof(float) * 5 * G4));
-    CK(cudaMalloc(&h->d_whh_t, sizeof(float) * H * G4));
     CK(cudaMalloc(&h->d_whh_r_t, sizeof(float) * H * G4));
+    {                                              // the fp32 kernel's image: the four gates of a unit in one 16-byte word
+        std::vector<float> g4((size_t)H * G4);
+        for (int k = 0; k < H; ++k)
+            for (int u = 0; u < H; ++u)
+                for (int g = 0; g < 4; ++g) g4[((size_t)k * H + u) * 4 + g] = w_hh_f[(size_t)(g * H + u) * H + k];
+        CK(cudaMalloc(&h->d_whh_g4, sizeof(float) * H * G4));
+        CK(cudaMemcpy(h->d_whh_g4, g4.data(), sizeof(float) * H * G4, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&h->d_wout, sizeof(float) * 2 * 2 * H));
     CK(cudaMalloc(&h->d_bout, sizeof(float) * 2));
     CK(cudaMalloc(&h->d_revlut, sizeof(float) * RD_MAX_LEN * 5 * 2));
@@ -119,7 +123,6 @@ extern "C" int rd_create(int device,
     CK(cudaMalloc(&h->d_ctrl, sizeof(int32_t) * 8));
     CK(cudaMemcpy(h->d_tab_f, tab_f.data(), sizeof(float) * 5 * G4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_tab_r, tab_r.data(), sizeof(float) * 5 * G4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_whh_t, whh_t.data(), sizeof(float) * H * G4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_whh_r_t, whh_r_t.data(), sizeof(float) * H * G4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_wout, w_out, sizeof(float) * 2 * 2 * H, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_bout, b_out, sizeof(float) * 2, cudaMemcpyHostToDevice));
@@ -151,7 +154,7 @@ extern "C" void rd_destroy(rd_handle* h) {
     rd_tc_destroy(h);
     rd_fq_destroy(h);
     free_scratch(h);
-    cudaFree(h->d_tab_f); cudaFree(h->d_tab_r); cudaFree(h->d_whh_t); cudaFree(h->d_whh_r_t);
+    cudaFree(h->d_tab_f); cudaFree(h->d_tab_r); cudaFree(h->d_whh_r_t); cudaFree(h->d_whh_g4);
     cudaFree(h->d_wout); cudaFree(h->d_bout); cudaFree(h->d_revlut); cudaFree(h->d_lutstate);
     cudaFree(h->d_hist); cudaFree(h->d_cursor); cudaFree(h->d_ctrl); cudaFree(h->d_blocksum);
     for (int e = 0; e < 2; ++e)
@@ -252,9 +255,9 @@ static float band_tau(int precision, int max_len) {
 int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                            int semantics, int precision, float* d_logits, float* d_probs,
                            int8_t* d_labels, int64_t* d_counts, cudaStream_t st, int ostride) {
-    const bool generic = h->hidden != RD_H;        // another hidden size: every precision runs the generic fp32 kernel
-    const bool need_codes = precision == RD_PREC_FP32 && !generic;
-    int rc = ensure_scratch(h, n, max_len, need_codes);
+    // fp32, and every precision of a handle with a hidden size other than 128, run the fp32 CUDA-core kernel
+    const bool fp32 = h->hidden != RD_H || precision == RD_PREC_FP32;
+    int rc = ensure_scratch(h, n);
     if (rc) return rc;
     if (semantics == RD_SEM_PADDED && max_len > h->lut_rows) {      // krev < max_len: extend the reverse-direction table
         rc = rd_build_reverse_lut(h, max_len, st);
@@ -263,13 +266,12 @@ int rd_classify_device(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off,
     int64_t tiles = 0;
     {
         StageTimer tm(h, 0, st);
-        rc = rd_launch_plan(h, d_seq, d_off, n, max_len, semantics, need_codes, &tiles, st, ostride);
+        rc = rd_launch_plan(h, d_seq, d_off, n, max_len, semantics, &tiles, st, ostride);
     }
     if (rc) return rc;
     {
         StageTimer tm(h, 1, st);
-        if (generic) rc = rd_launch_lstm_generic(h, d_seq, d_off, tiles, max_len, d_logits, st, ostride);
-        else if (precision == RD_PREC_FP32) rc = rd_launch_lstm_simt(h, tiles, max_len, d_logits, st);
+        if (fp32) rc = rd_launch_lstm_fp32(h, d_seq, d_off, tiles, max_len, d_logits, st, ostride);
         else if (precision == RD_PREC_TC_AUTO || precision == RD_PREC_TC_MIXED) {
             // two passes: the cheaper kernel over everything, then the exact kernel over the reads whose margin from the
             // first pass is inside a band several times the first pass's error bound (their slots are compacted on the
@@ -300,7 +302,7 @@ int rd_pair_none_refine(rd_handle* h, const uint8_t* const d_seq[2], const int64
     int rc = ensure_band(h);
     for (int e = 0; e < 2 && !rc; ++e) {
         int64_t tiles = 0;
-        rc = rd_launch_plan(h, d_seq[e], d_off[e], n, max_len, semantics, false, &tiles, st, ostride);   // (the ends share the scratch)
+        rc = rd_launch_plan(h, d_seq[e], d_off[e], n, max_len, semantics, &tiles, st, ostride);   // (the ends share the scratch)
         if (!rc) rc = rd_launch_band_select(h, d_logits[e], tiles, tau, st, d_logits[1 - e]);
         const int64_t nb = (tiles * RD_TILE + 255) / 256;
         if (!rc) rc = rd_launch_lstm_tc(h, d_seq[e], d_off[e], tiles, max_len, RD_PREC_TC_EXACT, d_logits[e], st, h->d_splan2,
@@ -410,7 +412,7 @@ static int classify_host_run(rd_handle* h, int ends,
             max_bytes = std::max(max_bytes, off[e][cut[c + 1]] - off[e][cut[c]]);
     rc = ensure_stage(h, chunk, max_bytes, ends, probs != nullptr);
     if (rc) return rc;
-    rc = ensure_scratch(h, chunk, max_len, precision == RD_PREC_FP32 && h->hidden == RD_H);
+    rc = ensure_scratch(h, chunk);
     if (rc) return rc;
     RD_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(int64_t) * 4, h->s_cmp));
 

@@ -46,16 +46,16 @@ __device__ __forceinline__ uint32_t rd_base_code(uint32_t b) {
 struct rd_handle {
     int device = 0;
     int sm_count = 0;
-    int hidden = RD_H;             // hidden size of the loaded model; the tensor-core and tuned fp32 kernels need RD_H,
-                                   // any other multiple of 32 up to 256 runs on the generic fp32 kernel (rd_lstm_generic.cu)
-    bool generic_attr_set = false, lut_attr_set = false;
-    int generic_ctas_per_sm = 1;
+    int hidden = RD_H;             // hidden size of the loaded model; the tensor-core kernels need RD_H, any other
+                                   // multiple of 32 up to 256 runs every precision on the fp32 kernel (rd_lstm_fp32.cu)
+    bool fp32_attr_set = false, lut_attr_set = false;
+    int fp32_ctas_per_sm = 1;
     std::string err;
     int64_t launches = 0;
 
     // weights (device, fp32)
     float* d_tab_f = nullptr;      // [5][512] fwd gate-input table: W_ih^T rows + b_ih + b_hh; row 4 = bias only
-    float* d_whh_t = nullptr;      // [128][512] W_hh^T (k-major)
+    float* d_whh_g4 = nullptr;     // [H (k)][H (u)][4]: W_hh^T with the four gates of a unit adjacent (rd_lstm_fp32.cu)
     float* d_tab_r = nullptr;      // [5][512] reverse direction table
     float* d_whh_r_t = nullptr;    // [128][512]
     float* d_wout = nullptr;       // [2][256]
@@ -65,12 +65,10 @@ struct rd_handle {
     int lut_rows = 0;
     rd_tc_state* tc = nullptr;
     rd_fq_state* fq = nullptr;
-    bool simt_attr_set = false;
 
     // scratch
     int64_t cap_n = 0;             // reads
     int64_t cap_slots = 0;         // tiles*128
-    int64_t cap_codes = 0;         // bytes
     uint32_t* d_plan = nullptr;
     uint32_t* d_splan = nullptr;
     int32_t* d_perm = nullptr;
@@ -78,7 +76,6 @@ struct rd_handle {
     int32_t* d_perm2 = nullptr;
     int64_t* d_band = nullptr;     // [slots/256 + 2]: per-block band counts -> exclusive offsets; last = total
     int64_t cap_band = 0;
-    uint8_t* d_codes = nullptr;
     int32_t* d_hist = nullptr;     // [RD_MAX_LEN+2] histogram → bucket starts
     int32_t* d_cursor = nullptr;   // [RD_MAX_LEN+2]
     int32_t* d_ctrl = nullptr;     // [8]: 0 = status flags, 1 = work counter, 2 = max nfwd
@@ -118,11 +115,10 @@ struct rd_handle {
 
 // kernels' host launchers (each returns RD_OK / RD_ERR_*; all async on `st`)
 int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
-                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st, int ostride = 1);
+                   int semantics, int64_t* n_tiles_out, cudaStream_t st, int ostride = 1);
 int rd_launch_onehot(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int max_len,
                      int layout, float* d_out, int64_t* d_row_off, cudaStream_t st);
-int rd_launch_lstm_simt(rd_handle* h, int64_t n_tiles, int max_len, float* d_logits, cudaStream_t st);
-int rd_launch_lstm_generic(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
+int rd_launch_lstm_fp32(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
                            float* d_logits, cudaStream_t st, int ostride = 1);
 int rd_launch_lstm_tc(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n_tiles, int max_len,
                       int precision, float* d_logits, cudaStream_t st, const uint32_t* d_splan = nullptr,

@@ -115,59 +115,6 @@ scatter_kernel(const uint32_t* __restrict__ plan, int64_t n, const int32_t* __re
     }
 }
 
-// codes: one CTA per tile; transposes [read][t] bytes into [t][read] code lines via smem
-__global__ void __launch_bounds__(256)
-codes_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int ostride,
-             const int32_t* __restrict__ perm, const uint32_t* __restrict__ splan, int L,
-             uint8_t* __restrict__ codes) {
-    __shared__ __align__(16) uint8_t tile[128][RD_TILE + 4];
-    __shared__ int64_t s_beg[RD_TILE];
-    __shared__ int s_len[RD_TILE];
-    int64_t tileid = blockIdx.x;
-    int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < RD_TILE) {
-        int32_t r = perm[tileid * RD_TILE + tid];
-        if (r >= 0) {
-            int64_t b = off[(int64_t)r * ostride];
-            int64_t l = off[(int64_t)r * ostride + 1] - b;
-            s_beg[tid] = b;
-            s_len[tid] = (int)(l < (int64_t)L ? l : (int64_t)L);
-        } else {
-            s_beg[tid] = 0;
-            s_len[tid] = 0;
-        }
-    }
-    int T = (int)PLAN_NFWD(splan[tileid * RD_TILE]);   // slots are sorted descending
-    __syncthreads();
-    uint8_t* out = codes + tileid * (int64_t)L * RD_TILE;
-    for (int t0 = 0; t0 < T; t0 += 128) {
-        // each warp loads 16 reads, 32 consecutive bases per instruction
-        for (int rr = 0; rr < 16; ++rr) {
-            int r = warp * 16 + rr;
-            int64_t b = s_beg[r];
-            int len = s_len[r];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int t = t0 + q * 32 + lane;
-                uint32_t c = 4u;
-                if (t < len) c = base_code(seq[b + t]);
-                tile[q * 32 + lane][r] = (uint8_t)c;
-            }
-        }
-        __syncthreads();
-        // write 128-B lines: thread → (row = tid/32 + 8*j, 4 bytes at lane*4)
-        for (int j = 0; j < 16; ++j) {
-            int row = (tid >> 5) + 8 * j;
-            int t = t0 + row;
-            if (t < T) {
-                uint32_t v = *reinterpret_cast<const uint32_t*>(&tile[row][lane * 4]);
-                *reinterpret_cast<uint32_t*>(out + (int64_t)t * RD_TILE + lane * 4) = v;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // one-hot materialisation (parity artefact of the reference encoders)
 // A write-only stream of 16 B per base.  Every store instruction of a warp covers 32 CONSECUTIVE rows (512 contiguous
@@ -322,7 +269,7 @@ onehot_ragged_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int64_t n, int L,
-                   int semantics, bool need_codes, int64_t* n_tiles_out, cudaStream_t st, int ostride) {
+                   int semantics, int64_t* n_tiles_out, cudaStream_t st, int ostride) {
     int64_t tiles = (n + RD_TILE - 1) / RD_TILE;
     *n_tiles_out = tiles;
     if (n == 0) return RD_OK;
@@ -342,8 +289,7 @@ int rd_launch_plan(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off, int
     int kspan = L + 1;
     scatter_kernel<<<nb, 256, sizeof(int32_t) * 2 * kspan, st>>>(h->d_plan, n, h->d_hist, h->d_cursor,
                                                                  h->d_perm, h->d_splan, 0, kspan);
-    if (need_codes) codes_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_seq, d_off, ostride, h->d_perm, h->d_splan, L, h->d_codes);
-    h->launches += need_codes ? 4 : 3;
+    h->launches += 3;
     RD_CUDA(h, cudaGetLastError());
     return RD_OK;
 }

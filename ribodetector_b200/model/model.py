@@ -57,7 +57,7 @@ class SeqModel:
     """BiLSTM(4→H) + Linear(2H→2) classifier.  ``model(x)`` returns raw logits ``[B, 2]``.  H = 128 (the shipped
     checkpoint, ``config.json``) runs on the tensor-core kernels in the chosen ``precision``; any other multiple of 32 up to
     256 — ``SeqModel(**arch.args)`` in the reference takes any ``hidden_size``, ``model/model.py:11-29`` — runs on the
-    generic fp32 CUDA-core kernel whatever the ``precision``."""
+    fp32 CUDA-core kernel whatever the ``precision``."""
 
     def __init__(self, input_size=4, hidden_size=128, num_layers=1, num_classes=2,
                  batch_first=True, bidirectional=True, pack_seq=True, precision="tc_mixed"):
@@ -66,7 +66,7 @@ class SeqModel:
                              "batch_first=True, bidirectional=True (the shipped architecture)")
         if hidden_size % 32 != 0 or not 32 <= hidden_size <= 256:
             raise ValueError("SeqModel kernels take hidden_size = a multiple of 32 between 32 and 256 (128, the shipped "
-                             "size, runs on the tensor-core kernels; any other on the generic fp32 kernel)")
+                             "size, runs on the tensor-core kernels; any other on the fp32 CUDA-core kernel)")
         if precision not in _lib.PREC:
             raise ValueError("precision must be one of %s" % sorted(_lib.PREC))
         self.hidden_size = hidden_size

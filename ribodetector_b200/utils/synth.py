@@ -85,7 +85,7 @@ def fastq_text(n, length, seed, n_frac=0.001):
 def synth_weights(hidden_size, seed, gain=3.5):
     """A seeded random checkpoint of the reference architecture at another hidden size (state_dict keys of
     ``model/model.py:16-24``): U(-g/sqrt(H), g/sqrt(H)) like ``nn.LSTM``'s default init, times `gain` so that gates
-    leave the linear range.  Used by oracle/gen_golden_arch.py and by the tests of the generic-H kernel — the
+    leave the linear range.  Used by oracle/gen_golden_arch.py and by the tests of the other hidden sizes — the
     reference ships one checkpoint (H = 128) only."""
     rng = np.random.Generator(np.random.PCG64([seed, hidden_size]))
     H = hidden_size

@@ -639,7 +639,7 @@ def _arch_model(H, precision="fp32"):
 @pytest.mark.parametrize("semantics", ["packed", "padded"])
 def test_other_hidden_sizes_match_reference_golden(H, semantics):
     """The reference's own SeqModel / model_cpu.SeqModel instantiated at another hidden_size with seeded weights
-    (oracle/gen_golden_arch.py): fp32 bounds, every precision name (they all run the generic fp32 kernel)."""
+    (oracle/gen_golden_arch.py): fp32 bounds, every precision name (they all run the fp32 CUDA-core kernel)."""
     m, _w, g = _arch_model(H)
     try:
         L = int(g["max_len"])

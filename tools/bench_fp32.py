@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Throughput of the generic-H fp32 kernel (rd_lstm_generic.cu) at hidden sizes other than the shipped 128, beside the
-H = 128 fp32 CUDA-core kernel on the same reads: device-resident 100 bp reads, CUDA-event timed, 3 warm-up + 5 timed
-calls per size.    python tools/bench_generic.py [n_reads] -> profiles/r2_generic_hidden.json"""
+"""Throughput of the fp32 CUDA-core kernel (rd_lstm_fp32.cu) over the hidden sizes it takes (the shipped 128 included):
+device-resident 100 bp reads, CUDA-event timed, 3 warm-up + 5 timed calls per size.
+    python tools/bench_fp32.py [n_reads] -> profiles/r2_fp32_hidden.json"""
 import json
 import os
 import sys
@@ -34,12 +34,12 @@ def main():
             m.classify(d_seq, d_off, 100)
         torch.cuda.synchronize()
         ms = m.get_timing()["lstm"][0] / 5
-        fma = 8.0 * H * H * 100 * n          # 4H x H MACs per read-step
-        out["sizes"][str(H)] = {"kernel": "lstm_simt_kernel (H = 128 tuned)" if H == 128 else "lstm_generic_kernel",
+        fma = 4.0 * H * H * 100 * n          # 4H x H multiply-adds per read-step
+        out["sizes"][str(H)] = {"kernel": "lstm_fp32_kernel",
                                 "ms": ms, "reads_per_s": n / ms * 1e3, "fp32_tflops": 2 * fma / ms / 1e9}
         print(H, out["sizes"][str(H)], flush=True)
         m.close()
-    with open(os.path.join(ROOT, "profiles", "r2_generic_hidden.json"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", "r2_fp32_hidden.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 

@@ -9,7 +9,8 @@ from ribodetector_b200.utils.weights import load_weights
 prec = sys.argv[1] if len(sys.argv) > 1 else "tc_mixed"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 ls = sys.argv[3] if len(sys.argv) > 3 else "100"
-m = SeqModel(precision=prec); m.load_state_dict(load_weights()); m.to("cuda:0")
+H = int(os.environ.get("RD_NCU_HIDDEN", "128"))          # another hidden size: the fp32 CUDA-core kernel on seeded weights
+m = SeqModel(hidden_size=H, precision=prec); m.load_state_dict(load_weights() if H == 128 else synth.synth_weights(H, 7)); m.to("cuda:0")
 if "-" in ls:
     lo, hi = (int(x) for x in ls.split("-"))
     seq, off = synth.synth_reads(n, lo, hi, synth.SEED_BASE + 5)
