@@ -107,12 +107,12 @@ extern "C" int rd_create(int device,
     CK(cudaMalloc(&h->d_tab_r, sizeof(float) * 5 * G4));
     CK(cudaMalloc(&h->d_whh_r_t, sizeof(float) * H * G4));
     {                                              // the fp32 kernel's image: the four gates of a unit in one 16-byte word
-        std::vector<float> g4((size_t)H * G4);
+        std::vector<float> g4((size_t)(H + 1) * G4, 0.0f);      // + one zero row: the kernel prefetches one k ahead
         for (int k = 0; k < H; ++k)
             for (int u = 0; u < H; ++u)
                 for (int g = 0; g < 4; ++g) g4[((size_t)k * H + u) * 4 + g] = w_hh_f[(size_t)(g * H + u) * H + k];
-        CK(cudaMalloc(&h->d_whh_g4, sizeof(float) * H * G4));
-        CK(cudaMemcpy(h->d_whh_g4, g4.data(), sizeof(float) * H * G4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&h->d_whh_g4, sizeof(float) * (H + 1) * G4));
+        CK(cudaMemcpy(h->d_whh_g4, g4.data(), sizeof(float) * (H + 1) * G4, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&h->d_wout, sizeof(float) * 2 * 2 * H));
     CK(cudaMalloc(&h->d_bout, sizeof(float) * 2));

@@ -26,14 +26,16 @@ constexpr int GEN_PAD = 4;              // h row = 16 S + 4 floats: 16-byte stor
 
 // Gates: expf (2 ulp) and an approximate-reciprocal division (2 ulp), branch-free.  tanh as 1 - 2 / (e^2x + 1): absolute
 // error <= 2e-7 everywhere (the relative error grows for |x| -> 0, where the value itself vanishes) — the same size as
-// the rounding of the 128-term fp32 dot products that feed it; e^2x = inf gives 1, e^2x = 0 gives -1.
+// the rounding of the H-term fp32 dot products that feed it; e^2x = inf gives 1, e^2x = 0 gives -1.
+// (Measured and dropped: the gates straight from ex2.approx / rcp.approx — 5 % faster, but the kernel's error against the
+// fp64 oracle grows from 1.15e-5 to 1.8e-5 at 100 bp, and this kernel is the arbiter of the tensor-core modes.)
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) { return 1.0f - __fdividef(2.0f, expf(2.0f * x) + 1.0f); }
 
 __global__ void __launch_bounds__(GEN_THREADS, 1)
 lstm_fp32_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ off, int ostride,
                     const uint32_t* __restrict__ splan, const int32_t* __restrict__ perm, int L, int64_t n_slots, int H, int S,
-                    const float4* __restrict__ whh_g4,  // [H (k)][H (u)] {i, f, g, o}
+                    const float4* __restrict__ whh_g4,  // [H + 1 (k; the last row is padding)][H (u)] {i, f, g, o}
                     const float* __restrict__ tab,      // [5][4H]
                     const float* __restrict__ wout,     // [2][2H]
                     const float* __restrict__ bout, const float* __restrict__ revlut, float* __restrict__ logits) {
@@ -93,11 +95,15 @@ lstm_fp32_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ of
 #pragma unroll
                 for (int g = 0; g < 4; ++g) acc[g][r] = tr[g * H];
             }
-            float4 w = __ldg(whh_g4 + u);
+            const float4* wp = whh_g4 + u;                    // row k of the image; row H is padding for the last prefetch
+            const float* hp = hc;
+            float4 w = __ldg(wp);
 #pragma unroll 2
             for (int k = 0; k < H; ++k) {
-                const float4 wn = __ldg(whh_g4 + (int64_t)(k + 1 < H ? k + 1 : k) * H + u);     // one k ahead
-                const float4* hk = reinterpret_cast<const float4*>(hc + k * HROW);
+                wp += H;
+                const float4 wn = __ldg(wp);                  // one k ahead
+                const float4* hk = reinterpret_cast<const float4*>(hp);
+                hp += HROW;
 #pragma unroll
                 for (int r4 = 0; r4 < GEN_C / 4; ++r4) {
                     const float4 hv = hk[r4];
@@ -114,18 +120,19 @@ lstm_fp32_kernel(const uint8_t* __restrict__ seq, const int64_t* __restrict__ of
             }
 #pragma unroll
             for (int r4 = 0; r4 < GEN_C / 4; ++r4) {
+                const float4 ho4 = *reinterpret_cast<const float4*>(hc + u * HROW + 4 * r4);   // a finished read keeps its state
+                const float ho[4] = {ho4.x, ho4.y, ho4.z, ho4.w};
                 float hv[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int r = 4 * r4 + q;
-                    if (t < nf_s[r0 + r]) {
-                        const float ig = sigmoid_acc(acc[0][r]), fg = sigmoid_acc(acc[1][r]);
-                        const float gg = tanh_acc(acc[2][r]), og = sigmoid_acc(acc[3][r]);
-                        c[r] = fmaf(fg, c[r], ig * gg);
-                        hv[q] = og * tanh_acc(c[r]);
-                    } else {
-                        hv[q] = hc[u * HROW + r];          // a finished read keeps its state
-                    }
+                    const bool act = t < nf_s[r0 + r];
+                    const float ig = sigmoid_acc(acc[0][r]), fg = sigmoid_acc(acc[1][r]);
+                    const float gg = tanh_acc(acc[2][r]), og = sigmoid_acc(acc[3][r]);
+                    const float cn = fmaf(fg, c[r], ig * gg);
+                    const float hn1 = og * tanh_acc(cn);
+                    c[r] = act ? cn : c[r];
+                    hv[q] = act ? hn1 : ho[q];
                 }
                 *reinterpret_cast<float4*>(hn + u * HROW + r0 + 4 * r4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
