@@ -22,6 +22,7 @@ namespace {
 
 constexpr int GEN_C = 16;               // reads per thread
 constexpr int GEN_THREADS = 512;        // at most (S = GEN_THREADS / H subgroups of H threads)
+constexpr size_t GEN_SMEM_MAX = 100 * 1024;   // >= the dynamic shared memory of every supported H
 constexpr int GEN_PAD = 4;              // h row = 16 S + 4 floats: 16-byte stores of consecutive units hit distinct banks
 
 // Gates: expf (2 ulp) and an approximate-reciprocal division (2 ulp), branch-free.  tanh as 1 - 2 / (e^2x + 1): absolute
@@ -174,8 +175,11 @@ int rd_launch_lstm_fp32(rd_handle* h, const uint8_t* d_seq, const int64_t* d_off
     const int RPC = GEN_C * S;
     const size_t smem = sizeof(float) * (2 * (size_t)H * (RPC + GEN_PAD) + 20 * (size_t)H) + sizeof(int) * 6 * (size_t)RPC +
                         sizeof(int64_t) * (size_t)RPC;
+    if (smem > GEN_SMEM_MAX) { h->err = "rd_lstm_fp32: shared memory budget exceeded"; return RD_ERR_UNSUPPORTED; }
     if (!h->fp32_attr_set) {
-        RD_CUDA(h, cudaFuncSetAttribute(lstm_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the attribute belongs to the function on this device, not to the handle: handles of different hidden sizes share
+        // it, so it is always set to the largest size any H needs (H = 256: 95 KB)
+        RD_CUDA(h, cudaFuncSetAttribute(lstm_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_MAX));
         int per_sm = 1;
         RD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_fp32_kernel, H * S, smem));
         h->fp32_ctas_per_sm = per_sm > 0 ? per_sm : 1;

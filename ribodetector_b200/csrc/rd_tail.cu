@@ -228,7 +228,8 @@ int rd_build_reverse_lut(rd_handle* h, int rows, cudaStream_t st) {
     const int H = h->hidden;
     const size_t smem = sizeof(double) * (size_t)(27 * H);           // h, c, z[5][4H], hrev[5][H]
     if (!h->lut_attr_set) {
-        RD_CUDA(h, cudaFuncSetAttribute(reverse_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (the attribute belongs to the function on this device, not to the handle: always the largest size, H = 256)
+        RD_CUDA(h, cudaFuncSetAttribute(reverse_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 27 * 256)));
         h->lut_attr_set = true;
     }
     reverse_lut_kernel<<<1, 4 * H, smem, st>>>(h->d_whh_r_t, h->d_tab_r, h->d_wout, H, h->lut_rows, rows, h->d_lutstate, h->d_revlut);

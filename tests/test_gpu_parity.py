@@ -685,3 +685,28 @@ def test_other_hidden_sizes_ragged_reads_host_api_and_pairs(H):
             assert np.array_equal(lab[sure], want[sure]), mode
     finally:
         m.close()
+
+
+def test_handles_of_different_hidden_sizes_coexist(gpu_model):
+    """Function attributes (dynamic shared memory limits) are per device, not per handle: a small-H handle created after a
+    large-H one must not shrink what the large one may launch with — fp32 classify and a reverse-LUT extension (padded
+    semantics beyond 512 steps) on the older handles after the younger ones were used."""
+    g = load_golden("arch")
+    L = int(g["max_len"])
+    big, _w, _ = _arch_model(256)
+    try:
+        a = big.classify(g["seq"], g["off"], L)[0].cpu().numpy()
+        small, _w2, _ = _arch_model(32)
+        try:
+            small.classify(g["seq"], g["off"], L)
+            small.classify(g["seq"], g["off"], 700, semantics="padded")
+        finally:
+            small.close()
+        b = big.classify(g["seq"], g["off"], L)[0].cpu().numpy()
+        assert np.array_equal(a, b)
+        big.classify(g["seq"], g["off"], 900, semantics="padded")             # extends the 256-unit handle's reverse LUT
+        check_logits(b, g["logits_packed_h256"], "fp32", L)
+        g1 = load_golden("se_L100")
+        check_logits(gpu_model.classify(g1["seq"], g1["off"], 100, precision="fp32")[0].cpu().numpy(), g1["logits_packed"], "fp32")
+    finally:
+        big.close()
