@@ -500,47 +500,106 @@ part_copy_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ re
         s_dst[tid] = blockbase[(int64_t)blockIdx.x * 3 + cls] + before + (incl[cls] - mine[cls]);
     }
     __syncthreads();
-    const int sub = lane >> 4, hl = lane & 15;   // two records in flight per warp: twice the loads outstanding
+    if (nlines == 4) {
+        // FASTQ.  A record nothing was stripped from is ONE contiguous range of the input, and so is a RUN of such records
+        // that follow each other in the text and carry the same label: their texts (closing newlines included) are adjacent
+        // in the input and land adjacent in the output.  With a few per cent of the reads labelled rRNA a warp's 32 records
+        // are two or three runs of several KB: each is copied by the whole warp as 16-byte words aligned on the OUTPUT, the
+        // input words realigned with funnel shifts (two aligned 16-byte loads per store; the second one hits L1).
+        const int slot = warp * 32 + lane;
+        const bool valid = r0 + slot < n;
+        longlong2 a = make_longlong2(0, 0), d = a;
+        bool plain = false;
+        int mycls = -1;
+        if (valid) {
+            a = s_rec[slot][0];
+            const longlong2 b2 = s_rec[slot][1], c2 = s_rec[slot][2];
+            d = s_rec[slot][3];
+            plain = a.y + 1 == b2.x && b2.y + 1 == c2.x && c2.y + 1 == d.x;
+            mycls = label_class(labels[r0 + slot]);
+        }
+        const long long pend = __shfl_up_sync(0xffffffffu, d.y, 1);         // previous record: end of its quality line,
+        const int pcls = __shfl_up_sync(0xffffffffu, mycls, 1);            // its class, and whether it is plain
+        const int pplain = __shfl_up_sync(0xffffffffu, (int)plain, 1);
+        const bool joined = lane > 0 && valid && plain && pplain && pcls == mycls && pend + 1 == a.x;
+        uint32_t heads = __ballot_sync(0xffffffffu, valid && !joined);
+        while (heads) {
+            const int first = __ffs(heads) - 1;
+            heads &= heads - 1;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            const int stop = heads ? __ffs(heads) - 1 : 32 - __clz(vmask);   // one past the run's last record
+            const long long src0 = __shfl_sync(0xffffffffu, a.x, first);
+            const long long end = __shfl_sync(0xffffffffu, d.y, stop - 1);
+            const int is_plain = __shfl_sync(0xffffffffu, (int)plain, first);
+            uint8_t* o = out + s_dst[warp * 32 + first];
+            if (is_plain) {
+                const uint8_t* src = buf + src0;
+                const int nbytes = (int)(end - src0);                        // up to, not including, the last closing '\n'
+                int head = (int)((16u - (uint32_t)(uintptr_t)o) & 15u);
+                if (head > nbytes) head = nbytes;
+                if (lane < head) o[lane] = src[lane];
+                const int nvec = (nbytes - head) >> 4;
+                const uint8_t* s2 = src + head;
+                const uint32_t sh = (uint32_t)(uintptr_t)s2 & 15u, ws = sh >> 2, bs = 8u * (sh & 3u);
+                const uint4* sa = reinterpret_cast<const uint4*>(s2 - sh);
+                uint4* ov = reinterpret_cast<uint4*>(o + head);
+                // four independent 512-byte rows of the run in flight per warp (all loads first, then the stores)
+                for (int v0 = lane; v0 < nvec; v0 += 128) {
+                    uint4 A[4], B[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int v = v0 + 32 * q;
+                        A[q] = v < nvec ? __ldg(sa + v) : make_uint4(0u, 0u, 0u, 0u);
+                        B[q] = (sh && v < nvec) ? __ldg(sa + v + 1) : make_uint4(0u, 0u, 0u, 0u);   // (the aligned word holding the vector's last bytes)
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int v = v0 + 32 * q;
+                        uint32_t w0, w1, w2, w3, w4;
+                        if (ws == 0) { w0 = A[q].x; w1 = A[q].y; w2 = A[q].z; w3 = A[q].w; w4 = B[q].x; }
+                        else if (ws == 1) { w0 = A[q].y; w1 = A[q].z; w2 = A[q].w; w3 = B[q].x; w4 = B[q].y; }
+                        else if (ws == 2) { w0 = A[q].z; w1 = A[q].w; w2 = B[q].x; w3 = B[q].y; w4 = B[q].z; }
+                        else { w0 = A[q].w; w1 = B[q].x; w2 = B[q].y; w3 = B[q].z; w4 = B[q].w; }
+                        if (v < nvec)
+                            __stcs(ov + v, make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs),
+                                                      __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs)));
+                    }
+                }
+                const int done = head + 16 * nvec;
+                if (lane < nbytes - done) o[done + lane] = src[done + lane];
+                if (lane == 0) o[nbytes] = (uint8_t)'\n';
+            } else {
+                // a record with stripped line ends (CRLF, trailing blanks): byte by byte through its four line ranges
+                const int s1 = warp * 32 + first;
+                const longlong2 ra = s_rec[s1][0], rb = s_rec[s1][1], rc = s_rec[s1][2], rd = s_rec[s1][3];
+                const int t0 = (int)(ra.y - ra.x) + 1, t1 = t0 + (int)(rb.y - rb.x) + 1;
+                const int t2 = t1 + (int)(rc.y - rc.x) + 1, t3 = t2 + (int)(rd.y - rd.x) + 1;
+                for (int j = lane; j < t3; j += 32) {     // output byte j: which line it belongs to, or the '\n' closing one
+                    int64_t sp; int e2;
+                    if (j < t0) { sp = ra.x + j; e2 = t0; }
+                    else if (j < t1) { sp = rb.x + (j - t0); e2 = t1; }
+                    else if (j < t2) { sp = rc.x + (j - t1); e2 = t2; }
+                    else { sp = rd.x + (j - t2); e2 = t3; }
+                    o[j] = j == e2 - 1 ? (uint8_t)'\n' : buf[sp];
+                }
+            }
+        }
+        return;
+    }
+    // FASTA (two lines per record; the sequence lives in the joined region behind the text): half a warp per record
+    const int sub = lane >> 4, hl = lane & 15;
     for (int i = 0; i < 16; ++i) {
         if (r0 + warp * 32 + 2 * i >= n) break;
         const int slot = warp * 32 + 2 * i + sub;
         if (r0 + slot >= n) continue;
         const longlong2 a = s_rec[slot][0], b = s_rec[slot][1];
-        longlong2 c = s_rec[slot][2], d = s_rec[slot][3];
-        if (nlines == 2) { c = make_longlong2(0, 0); d = c; }
         const int t0 = (int)(a.y - a.x) + 1, t1 = t0 + (int)(b.y - b.x) + 1;
-        const int t2 = nlines == 2 ? t1 : t1 + (int)(c.y - c.x) + 1, t3 = nlines == 2 ? t1 : t2 + (int)(d.y - d.x) + 1;
         uint8_t* o = out + s_dst[slot];
-        if (nlines == 4 && a.y + 1 == b.x && b.y + 1 == c.x && c.y + 1 == d.x) {
-            // nothing was stripped: the record text is one contiguous range of the input plus the closing '\n'.
-            // Copy it as 4-byte words aligned on the OUTPUT; the input words are realigned with a funnel shift.
-            const uint8_t* src = buf + a.x;
-            const int nbytes = t3 - 1;
-            int head = (int)((4u - (uint32_t)(uintptr_t)o) & 3u);
-            if (head > nbytes) head = nbytes;
-            if (hl < head) o[hl] = src[hl];
-            const int nw = (nbytes - head) >> 2;
-            const uint8_t* s2 = src + head;
-            const uint32_t sh = (uint32_t)(uintptr_t)s2 & 3u;
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - sh);
-            uint32_t* ow = reinterpret_cast<uint32_t*>(o + head);
-            for (int w = hl; w < nw; w += 16) {
-                const uint32_t lo = sw[w];
-                const uint32_t hi = sh ? sw[w + 1] : 0u;      // (the aligned word holding the range's last bytes)
-                ow[w] = __funnelshift_r(lo, hi, 8u * sh);
-            }
-            const int done = head + 4 * nw;
-            if (hl < nbytes - done) o[done + hl] = src[done + hl];
-            if (hl == 0) o[nbytes] = (uint8_t)'\n';
-        } else {
-            for (int j = hl; j < t3; j += 16) {      // output byte j: which line it belongs to, or the '\n' closing one
-                int64_t src; int end;
-                if (j < t0) { src = a.x + j; end = t0; }
-                else if (j < t1) { src = b.x + (j - t0); end = t1; }
-                else if (j < t2) { src = c.x + (j - t1); end = t2; }
-                else { src = d.x + (j - t2); end = t3; }
-                o[j] = j == end - 1 ? (uint8_t)'\n' : buf[src];
-            }
+        for (int j = hl; j < t1; j += 16) {
+            int64_t src; int end;
+            if (j < t0) { src = a.x + j; end = t0; }
+            else { src = b.x + (j - t0); end = t1; }
+            o[j] = j == end - 1 ? (uint8_t)'\n' : buf[src];
         }
     }
 }
