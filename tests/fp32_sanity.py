@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A small run of the fp32 CUDA-core kernel (rd_lstm_fp32.cu) for compute-sanitizer: ragged reads at hidden sizes with
 1, 2, 5 and 8 read subgroups per CTA (named barriers / __syncwarp), checked against the fp64 oracle.
-    compute-sanitizer --tool racecheck python tools/fp32_sanity.py"""
+    compute-sanitizer --tool racecheck python tests/fp32_sanity.py"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from ribodetector_b200.model import SeqModel            # noqa: E402
 from ribodetector_b200.utils import synth               # noqa: E402
 from ribodetector_b200.utils.weights import load_weights  # noqa: E402
-from oracle.model_numpy import NumpyOracle              # noqa: E402  (a checker script, like smoke())
+from oracle.model_numpy import NumpyOracle              # noqa: E402  (tests/ may use the oracle as the checker)
 
 seq, off = synth.synth_reads(700, 1, 60, 99, n_frac=0.02)
 reads = synth.to_strings(seq, off)
