@@ -28,7 +28,9 @@ constexpr int GEN_PAD = 4;              // h row = 16 S + 4 floats: 16-byte stor
 // Gates: expf (2 ulp) and an approximate-reciprocal division (2 ulp), branch-free.  tanh as 1 - 2 / (e^2x + 1): absolute
 // error <= 2e-7 everywhere (the relative error grows for |x| -> 0, where the value itself vanishes) — the same size as
 // the rounding of the H-term fp32 dot products that feed it; e^2x = inf gives 1, e^2x = 0 gives -1.
-// (Measured and dropped: the gates straight from ex2.approx / rcp.approx — 5 % faster, but the kernel's error against the
+// (Measured and dropped: the FMAs issued as packed fma.rn.f32x2 — 27 % fewer issue slots in the k loop, bit-identical
+// results, no change in time (43.4 vs 43.1 TFLOP/s at H = 128): the loop is not bound by issue slots alone; and the gates
+// straight from ex2.approx / rcp.approx — 5 % faster, but the kernel's error against the
 // fp64 oracle grows from 1.15e-5 to 1.8e-5 at 100 bp, and this kernel is the arbiter of the tensor-core modes.)
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) { return 1.0f - __fdividef(2.0f, expf(2.0f * x) + 1.0f); }
