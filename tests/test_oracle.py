@@ -54,6 +54,27 @@ def test_numpy_oracle_matches_reference(case, numpy_oracle, weights):
     assert np.abs(got32 - g["logits_packed"]).max() <= 2e-4
 
 
+@pytest.mark.parametrize("H", [32, 64, 96, 192, 256])
+def test_oracles_match_reference_golden_at_other_hidden_sizes(H):
+    """The reference's own SeqModel / model_cpu.SeqModel instantiated at another hidden_size with seeded weights
+    (oracle/gen_golden_arch.py → tests/golden/arch.npz): both restatements are pinned at every size the kernels take."""
+    import torch
+    from oracle.model_torch import TorchOracle
+    from ribodetector_b200.utils import synth
+    torch.set_num_threads(1)
+    g = load_golden("arch")
+    assert H in g["hidden_sizes"].tolist()
+    w = synth.synth_weights(H, int(g["weight_seed"]))
+    reads = split_reads(g["seq"], g["off"])
+    L = int(g["max_len"])
+    o_t, o_n = TorchOracle(w, hidden_size=H), NumpyOracle(w, np.float64)
+    for sem in ("packed", "padded"):
+        ref = g["logits_%s_h%d" % (sem, H)]
+        assert np.abs(o_t.logits(reads, L, sem) - ref).max() <= 2e-6
+        assert np.abs(o_n.logits(reads, L, sem) - ref).max() <= 5e-5
+    assert np.abs(g["logits_packed_h%d" % H][:, 1] - g["logits_packed_h%d" % H][:, 0]).std() > 0.05     # not a degenerate model
+
+
 def test_packed_vs_padded_semantics_differ_on_short_reads(numpy_oracle):
     g = load_golden("se_L100")
     off = g["off"]
