@@ -3,6 +3,7 @@
 kernels were chosen from — the numbers DESIGN.md §10/§11 quote, reproducible without a GPU:
 
     python tests/prec_emulate.py [n_reads] [read_len]      -> table of max / p99.9 |dlogit| and |dp| vs the fp64 recurrence
+    RD_EMU_GATES=1 adds the e5m2 scheme with the correction products restricted to the columns of some gates
 
 Per step the gate pre-activations are  z = tab[code] + W_hh . h  with the product evaluated from ROUNDED operands as the
 scheme prescribes; activations, cell update and the FC are exact (fp64), so the table isolates operand rounding (what the
@@ -67,10 +68,14 @@ def e2m1_block(x, axis, block=32):
     return np.moveaxis(q.reshape(shp), -1, axis)
 
 
-def run(scheme, tab, whh_t, codes, nsteps):
-    """h after nsteps for every read; whh_t = W_hh^T [k, 4H]."""
+def run(scheme, tab, whh_t, codes, nsteps, gates="ifgo"):
+    """h after nsteps for every read; whh_t = W_hh^T [k, 4H].  `gates`: the gate columns that receive the correction
+    products (e5m2 scheme only) — would a correction pass over fewer than the 512 gate columns do?"""
     n = codes.shape[0]
     H = whh_t.shape[0]
+    gmask = np.zeros(4 * H)
+    for ch in gates:
+        gmask["ifgo".index(ch) * H:("ifgo".index(ch) + 1) * H] = 1.0
     h = np.zeros((n, H))
     c = np.zeros((n, H))
     W_hi = fp16(whh_t)
@@ -78,7 +83,7 @@ def run(scheme, tab, whh_t, codes, nsteps):
     if scheme in ("split3", "w_only"):
         W_lo_q = fp16(W_lo)
     elif scheme in ("e5m2", "mxf4_w"):
-        W_lo_q, W_hi_q = e5m2(W_lo), e5m2(W_hi)
+        W_lo_q, W_hi_q = e5m2(W_lo) * gmask[None, :], e5m2(W_hi) * gmask[None, :]
     elif scheme == "e4m3":
         W_lo_q, W_hi_q = e4m3(W_lo * 2.0 ** 12) * 2.0 ** -12, e4m3(W_hi)
     if scheme in ("mxf4", "mxf4_w"):
@@ -141,6 +146,13 @@ def main():
         d = np.abs(got - ref).max(1)
         print("%-8s %5d %12.2e %12.2e %12.2e" % (scheme, mmas, d.max(), np.quantile(d, 0.999), np.abs(softmax2(got) - pref).max()),
               flush=True)
+    if os.environ.get("RD_EMU_GATES"):          # e5m2 corrections over a subset of the gate columns only
+        print("e5m2 corrections applied to the columns of some gates only (all four: the e5m2 row above)")
+        for gates in ("fgo", "igo", "ifo", "ifg", "fg", "go", "if", "g", "f"):
+            got = logits(run("e5m2", orc.tab_f, orc.whh_f_t, codes, L, gates))
+            d = np.abs(got - ref).max(1)
+            print("%-8s %5s %12.2e %12.2e %12.2e" % (gates, "", d.max(), np.quantile(d, 0.999), np.abs(softmax2(got) - pref).max()),
+                  flush=True)
 
 
 if __name__ == "__main__":
